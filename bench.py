@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the DSTD-GCN training hot path on B200 (metric of BASELINE.json: train samples/s at the H3.6M shape).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload h36m|cmu|3dpw] [--impl reference]
+
+One "step" = one iteration of the reference engine loop (engine/prediction.py:215-294) on one batch of synthetic
+poses: forward on the batch, forward on the time-reversed batch (``inverse: True`` in every shipped config), MPJPE
+losses, one backward, gradient all-reduce (N > 1), Adam.  Under torchrun every rank runs its own shard
+(``--batch`` samples per GPU, weak scaling) and rank 0 prints ONE JSON line.
+
+``--impl reference`` times the reference's CPU implementation of the same step (the oracle port, all host threads)
+on a bounded sample of the workload; it never touches the GPU library.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (layout, V, T_in, T_out, dropout)  -- configs/dstdgcn/*.yaml of the reference
+    "h36m": ("h36m", 22, 10, 25, 0.1),
+    "cmu": ("cmu", 25, 10, 25, 0.1),
+    "3dpw": ("3dpw", 23, 10, 30, 0.0),
+}
+C_FEAT, N_LAYERS = 64, 5
+
+
+def algorithmic_bytes_per_pass(v, t, c=C_FEAT, layers=N_LAYERS):
+    """one HBM round trip per DSTDGCB layer, fp32, forward + backward of one model pass."""
+    chans = [(6, c)] + [(c, c)] * layers + [(c, 3)]
+    fwd = 4 * t * v * sum(ci + co for ci, co in chans)
+    bwd = 4 * t * v * sum(2 * ci + co for ci, co in chans)
+    return fwd + bwd
+
+
+def synthetic_batch(n, t, v, t_in, seed, scale_pose=1.0, scale_step=0.05):
+    """Seeded synthetic poses with the dataset's padding (dataset/h36m.py:53-57): a random walk per coordinate around a
+    per-joint offset; model-input frames t_in.. repeat the last observed frame; the inverse input is the time-reversed
+    window padded the same way.  Returns raw [N,T,3V] (inputs, inputs_inv, targets) on the CPU."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(n, 1, v * 3, generator=g) * scale_pose
+    walk = torch.cumsum(torch.randn(n, t, v * 3, generator=g) * scale_step, dim=1)
+    seq = base + walk
+    inputs = seq.clone()
+    inputs[:, t_in:] = seq[:, t_in - 1:t_in]
+    rev = torch.flip(seq, dims=[1])
+    inputs_inv = rev.clone()
+    inputs_inv[:, t_in:] = rev[:, t_in - 1:t_in]
+    return inputs.contiguous(), inputs_inv.contiguous(), seq.contiguous()
+
+
+def perturb(model):
+    """Make the dynamic-adjacency path live (alpha, W_s, R_t are zero at init)."""
+    import torch
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            leaf = k.split(".")[-1]
+            if leaf in ("alpha_sm", "alpha_tm"):
+                p.fill_(0.1)
+            elif leaf == "W_s":
+                p.fill_(0.05)
+            elif leaf == "R_t":
+                p.fill_(0.01)
+    return model
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =============================================================================================== CPU reference arm
+def cpu_reference_step_fn(workload, batch, threads):
+    """The reference's CPU path for one engine step (oracle port of engine/prediction.py:215-294 in fp32, torch CPU
+    kernels, all host threads)."""
+    import torch
+    from dstd_gcn_b200.model import dstdgcn as std
+    from oracle import dstd_oracle as orc
+    layout, v, t_in, t_out, _ = WORKLOADS[workload]
+    t = t_in + t_out
+    torch.set_num_threads(threads)
+    torch.manual_seed(777)
+    m = perturb(std.DSTDGCN(6, t_in, t_out, 0.0, v, C_FEAT, N_LAYERS, layout))
+    p = orc.state_from_module(m, torch.float32)
+    params = [x for x in p.values() if x.requires_grad]
+    opt = torch.optim.Adam(params, lr=3e-3)
+    inputs, inputs_inv, targets = synthetic_batch(batch, t, v, t_in, seed=777)
+
+    def step():
+        loss = orc.train_loss(p, inputs, inputs_inv, targets)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
+def time_cpu_reference(workload, batch, steps, warmup, threads):
+    step = cpu_reference_step_fn(workload, batch, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 32                      # the reference's own batch size (configs/dstdgcn/dstdgcn_h36m.yaml)
+    sps, sec = time_cpu_reference(args.workload, batch, args.steps, max(args.warmup, 1), threads)
+    layout, v, t_in, t_out, _ = WORKLOADS[args.workload]
+    sample = f"{args.steps} engine steps of batch {batch} (fp32, two forwards + backward + Adam each), oracle port"
+    line = {
+        "impl": "reference", "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch_override=batch),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, batch_override=None):
+    layout, v, t_in, t_out, drop = WORKLOADS[args.workload]
+    b = batch_override if batch_override is not None else args.batch
+    return {"workload": f"DSTD-GCN {args.workload} shape ({v} joints, {t_in}->{t_out} frames, xyz), C={C_FEAT}, "
+                        f"L={N_LAYERS}, training step with inverse pass, batch {b} per GPU",
+            "variant": "dstdgcn", "batch_per_gpu": b, "global_batch": b * args.gpus, "inverse": True,
+            "dropout": drop, "l2_policy": "per-step working set (activations + saved tensors) >> 126 MB L2; "
+                                          "inputs rotate over 4 distinct batches"}
+
+
+# =============================================================================================== GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--workload", default="h36m", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dstd_gcn_b200 import _lib
+    from dstd_gcn_b200.engine import TrainStep
+    from dstd_gcn_b200.model import dstdgcn as std
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    layout, v, t_in, t_out, drop = WORKLOADS[args.workload]
+    t = t_in + t_out
+    torch.manual_seed(777)                       # identical replicas on every rank
+    model = perturb(std.DSTDGCN(6, t_in, t_out, drop, v, C_FEAT, N_LAYERS, layout)).to(dev).train()
+    step = TrainStep(model, lr=3e-3, inverse=True)
+    be = _lib.backend()
+
+    nbuf = 4
+    host = [synthetic_batch(args.batch, t, v, t_in, seed=777 + rank * 1000 + i) for i in range(nbuf)]
+    host = [tuple(x.pin_memory() for x in b) for b in host]
+    resident = [tuple(x.to(dev) for x in b) for b in host]
+    stage = [tuple(torch.empty_like(x, device=dev) for x in host[0]) for _ in range(2)]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run_resident(k):
+        for i in range(k):
+            step(*resident[i % nbuf])
+
+    def run_e2e(k):
+        for i in range(k):
+            hb, db = host[i % nbuf], stage[i % 2]
+            for h, d in zip(hb, db):
+                d.copy_(h, non_blocking=True)
+            loss = step(*db)
+            loss_host.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the user reads the loss every step
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = be.launches
+        e0.record()
+        fn(k)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), be.launches - l0
+
+    run_resident(args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(run_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    run_e2e(2)
+    ms_e2e, _ = timed(run_e2e, args.steps)
+
+    if rank == 0:
+        total = args.batch * world * args.steps
+        sps = total / (ms * 1e-3)
+        sps_e2e = total / (ms_e2e * 1e-3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bytes_pass = algorithmic_bytes_per_pass(v, t)
+        passes_per_s_gpu = 2.0 * sps / world                      # inverse=True: two model passes per sample
+        achieved = passes_per_s_gpu * bytes_pass / 1e9
+        h2d = sum(x.numel() * 4 for x in host[0])
+        line = {
+            "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "model_passes_per_s": 2.0 * sps,
+            "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "scope": "whole training step per GPU: algorithmic bytes = one HBM round trip per DSTDGCB "
+                                  f"layer fwd+bwd = {bytes_pass} B per model pass (SURVEY.md 8d), 2 passes per sample",
+                         "algorithmic_bytes_per_sample": 2 * bytes_pass},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cb = 32
+            v_cpu, sec = time_cpu_reference(args.workload, cb, args.cpu_baseline_steps, 1, threads)
+            line["cpu_baseline"] = {"value": v_cpu, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_baseline_steps} engine steps of batch {cb} (same workload "
+                                              f"shape, fp32), {sec:.2f} s/step"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

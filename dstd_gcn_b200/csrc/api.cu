@@ -1,0 +1,332 @@
+// C ABI of libdstd_b200 (include/dstd_b200.h): argument validation, workspace carving and the kernel schedule of
+// the DSTD-GC unit (model/dstdgcn.py:80-94 as called from DSTDGCB.forward :145-150 / :157-161) and the 1x1 channel mix.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "kernels.cuh"
+
+namespace dstd {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return DSTD_ERR_CUDA;
+  }
+  return DSTD_OK;
+}
+
+struct GcWs {
+  float *wcat, *wm;                         // packed weights
+  float *gxa, *gxm, *gm;                    // backward intermediates
+  float *p_wcat, *p_wm, *p_wrm, *p_adj, *p_alpha;
+  int S1, S2;
+};
+
+static size_t gc_fwd_ws(int Cin, int Cout, int nb) {
+  return arena_need({(size_t)Cout * nb * (Cin + 1) * 4, (size_t)4 * nb * (Cin + 1) * 4});
+}
+static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
+  const size_t C1 = Cin + 1, G = (size_t)N * P * K;
+  const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N);
+  return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, G * nb * C1 * 4, G * nb * K * 4,
+                     G * nb * 4 * 4, (size_t)S1 * Cout * nb * C1 * 4, (size_t)S1 * 4 * nb * C1 * 4,
+                     (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4});
+}
+
+static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const dstd_branch* br, const char* fn) {
+  DSTD_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && P > 0 && K > 0, DSTD_ERR_BAD_ARG, "%s: non-positive dimension", fn);
+  DSTD_REQUIRE(nb >= 1 && nb <= DSTD_MAX_BRANCH, DSTD_ERR_BAD_ARG, "%s: nb=%d outside [1,%d]", fn, nb, DSTD_MAX_BRANCH);
+  for (int b = 0; b < nb; ++b)
+    DSTD_REQUIRE(br[b].w_m1 && br[b].b_m1 && br[b].w_m2 && br[b].b_m2 && br[b].w_rm && br[b].b_rm && br[b].w_f &&
+                     br[b].b_f && br[b].adj,
+                 DSTD_ERR_BAD_ARG, "%s: branch %d has a null weight", fn, b);
+  DSTD_REQUIRE(dynadj_supported(P, K) && aggregate_supported(Cin, P, K), DSTD_ERR_UNSUPPORTED,
+               "%s: unit shape P=%d K=%d outside the compiled tile limits (P<=40, K<=40)", fn, P, K);
+  return DSTD_OK;
+}
+
+static void fill_pack(PackParams& pk, int Cin, int Cout, int nb, const dstd_branch* br, float* wcat, float* wm) {
+  pk.Cin = Cin; pk.Cout = Cout; pk.nb = nb;
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+    const dstd_branch& s = br[b < nb ? b : 0];
+    pk.w_f[b] = s.w_f; pk.b_f[b] = s.b_f;
+    pk.w_m1[b] = s.w_m1; pk.b_m1[b] = s.b_m1;
+    pk.w_m2[b] = s.w_m2; pk.b_m2[b] = s.b_m2;
+  }
+  pk.wcat = wcat; pk.wm = wm;
+}
+
+static void fill_agg(AggParams& ag, int N, int Cin, int P, int K, int nb, int flags, const dstd_view& x,
+                     const float* pd, const float* alpha, const dstd_branch* br) {
+  ag.N = N; ag.Cin = Cin; ag.P = P; ag.K = K; ag.nb = nb;
+  ag.adj_t = (flags & DSTD_FLAG_ADJ_T) ? 1 : 0;
+  ag.x = mk(x);
+  ag.pd = pd;
+  ag.alpha = alpha;
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+    const dstd_branch& s = br[b < nb ? b : 0];
+    ag.adj[b] = s.adj; ag.adj_w[b] = s.adj_w; ag.adj_r[b] = s.adj_r;
+  }
+  ag.xa = nullptr; ag.gxa = nullptr; ag.gxm = nullptr;
+  ag.gx = View4{nullptr, 0, 0, 0, 0};
+}
+
+}  // namespace dstd
+
+using namespace dstd;
+
+extern "C" const char* dstd_last_error(void) { return g_err; }
+extern "C" const char* dstd_version(void) { return "dstd_b200 0.1 sm_100a"; }
+extern "C" int dstd_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" size_t dstd_gc_fwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb) {
+  (void)N; (void)P; (void)K;
+  return gc_fwd_ws(Cin, Cout, nb);
+}
+extern "C" size_t dstd_gc_bwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb) {
+  return gc_bwd_ws(N, Cin, Cout, P, K, nb);
+}
+
+// ---------------------------------------------------------------------------------------------- DSTD-GC forward
+extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) {
+  DSTD_REQUIRE(a, DSTD_ERR_BAD_ARG, "gc_forward: null args");
+  int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_forward");
+  if (rc) return rc;
+  DSTD_REQUIRE(a->x.ptr && a->out.ptr && a->m && a->pd && a->xa, DSTD_ERR_BAD_ARG, "gc_forward: null tensor");
+  DSTD_REQUIRE(a->ws && a->ws_bytes >= gc_fwd_ws(a->Cin, a->Cout, a->nb), DSTD_ERR_WORKSPACE,
+               "gc_forward: workspace too small (%zu < %zu)", a->ws_bytes, gc_fwd_ws(a->Cin, a->Cout, a->nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = a->N, Cin = a->Cin, Cout = a->Cout, P = a->P, K = a->K, nb = a->nb, C1 = Cin + 1;
+  const long long G = (long long)N * P * K;
+  Arena ar(a->ws, a->ws_bytes);
+  float* wcat = ar.take<float>((size_t)Cout * nb * C1);
+  float* wm = ar.take<float>((size_t)4 * nb * C1);
+
+  PackParams pk;
+  fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm);
+  if ((rc = launch_pack(pk, st))) return rc;
+
+  // 1. m = [conv_m1; conv_m2] x + b        (all branches in one pass over x)
+  BgemmParams g1;
+  g1.M = 4 * nb; g1.Kd = C1; g1.G = G; g1.P = P; g1.K = K;
+  g1.w = wm; g1.wsc = 1; g1.wsi = C1; g1.bias = nullptr;
+  g1.in = mk(a->x); g1.ones_row = Cin;
+  g1.out = dense_view(a->m, 4 * nb, P, K);
+  g1.add = View4{nullptr, 0, 0, 0, 0};
+  if ((rc = launch_bgemm(g1, st))) return rc;
+
+  // 2. pd = conv_rm(tanh(m1 - m2))         (pairwise tensor stays on chip)
+  DynAdjFwdParams dp;
+  dp.N = N; dp.P = P; dp.K = K; dp.nb = nb; dp.m = a->m; dp.pd = a->pd;
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+    dp.w_rm[b] = a->br[b < nb ? b : 0].w_rm;
+    dp.b_rm[b] = a->br[b < nb ? b : 0].b_rm;
+  }
+  if ((rc = launch_dynadj_fwd(dp, st))) return rc;
+
+  // 3. xa = [x;1] (alpha pd + A)           (aggregation before the channel mix)
+  AggParams ag;
+  fill_agg(ag, N, Cin, P, K, nb, a->flags, a->x, a->pd, a->alpha, a->br);
+  ag.xa = a->xa;
+  if ((rc = launch_aggregate_fwd(ag, st))) return rc;
+
+  // 4. out = [Wf_0 bf_0 | Wf_1 bf_1] xa (+ skip)
+  BgemmParams g2;
+  g2.M = Cout; g2.Kd = nb * C1; g2.G = G; g2.P = P; g2.K = K;
+  g2.w = wcat; g2.wsc = 1; g2.wsi = nb * C1; g2.bias = nullptr;
+  g2.in = dense_view(a->xa, nb * C1, P, K); g2.ones_row = -1;
+  g2.out = mk(a->out);
+  g2.add = mk(a->skip);
+  return launch_bgemm(g2, st);
+}
+
+// ---------------------------------------------------------------------------------------------- DSTD-GC backward
+extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream) {
+  DSTD_REQUIRE(a, DSTD_ERR_BAD_ARG, "gc_backward: null args");
+  int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_backward");
+  if (rc) return rc;
+  DSTD_REQUIRE(a->x.ptr && a->gout.ptr && a->gx.ptr && a->m && a->pd && a->xa, DSTD_ERR_BAD_ARG,
+               "gc_backward: null tensor");
+  const int N = a->N, Cin = a->Cin, Cout = a->Cout, P = a->P, K = a->K, nb = a->nb, C1 = Cin + 1;
+  const size_t need = gc_bwd_ws(N, Cin, Cout, P, K, nb);
+  DSTD_REQUIRE(a->ws && a->ws_bytes >= need, DSTD_ERR_WORKSPACE, "gc_backward: workspace too small (%zu < %zu)",
+               a->ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long G = (long long)N * P * K;
+  const int S1 = wgrad_splits(G), S2 = dynadj_bwd_splits(N);
+  Arena ar(a->ws, a->ws_bytes);
+  float* wcat = ar.take<float>((size_t)Cout * nb * C1);
+  float* wm = ar.take<float>((size_t)4 * nb * C1);
+  float* gxa = ar.take<float>((size_t)G * nb * C1);
+  float* gxm = ar.take<float>((size_t)G * nb * K);
+  float* gm = ar.take<float>((size_t)G * nb * 4);
+  float* p_wcat = ar.take<float>((size_t)S1 * Cout * nb * C1);
+  float* p_wm = ar.take<float>((size_t)S1 * 4 * nb * C1);
+  float* p_wrm = ar.take<float>((size_t)S2 * nb * P * (2 * P + 1));
+  float* p_adj = ar.take<float>((size_t)S2 * nb * K * K);
+  float* p_alpha = ar.take<float>((size_t)S2 * nb);
+
+  PackParams pk;
+  fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm);
+  if ((rc = launch_pack(pk, st))) return rc;
+
+  // 1. gxa = wcat^T gout
+  BgemmParams g1;
+  g1.M = nb * C1; g1.Kd = Cout; g1.G = G; g1.P = P; g1.K = K;
+  g1.w = wcat; g1.wsc = nb * C1; g1.wsi = 1; g1.bias = nullptr;
+  g1.in = mk(a->gout); g1.ones_row = -1;
+  g1.out = dense_view(gxa, nb * C1, P, K);
+  g1.add = View4{nullptr, 0, 0, 0, 0};
+  if ((rc = launch_bgemm(g1, st))) return rc;
+
+  // 2. g(wcat)[o, j] = sum gout[o] xa[j]
+  WgradParams w1;
+  w1.M = Cout; w1.Cd = nb * C1; w1.G = G; w1.P = P; w1.K = K;
+  w1.a = mk(a->gout);
+  w1.b = dense_view(const_cast<float*>(a->xa), nb * C1, P, K);
+  w1.b_ones_row = -1;
+  w1.partial = p_wcat;
+  if ((rc = launch_wgrad(w1, st))) return rc;
+  const int S1a = w1.S;
+
+  // 3. aggregation backward: gx (first contribution), gxm
+  AggParams ag;
+  fill_agg(ag, N, Cin, P, K, nb, a->flags, a->x, a->pd, a->alpha, a->br);
+  ag.gxa = gxa;
+  ag.gx = mk(a->gx);
+  ag.gxm = gxm;
+  if ((rc = launch_aggregate_bwd(ag, st))) return rc;
+
+  // 4. dynamic adjacency backward: gm, partial gWrm/gbrm, gA_eff, galpha
+  DynAdjBwdParams db;
+  db.N = N; db.P = P; db.K = K; db.nb = nb;
+  db.m = a->m; db.pd = a->pd; db.gxm = gxm; db.alpha = a->alpha; db.gm = gm;
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) db.w_rm[b] = a->br[b < nb ? b : 0].w_rm;
+  db.S = S2; db.part_wrm = p_wrm; db.part_adj = p_adj; db.part_alpha = p_alpha;
+  if ((rc = launch_dynadj_bwd(db, st))) return rc;
+
+  // 5. gx += wm^T gm
+  BgemmParams g2;
+  g2.M = Cin; g2.Kd = 4 * nb; g2.G = G; g2.P = P; g2.K = K;
+  g2.w = wm; g2.wsc = C1; g2.wsi = 1; g2.bias = nullptr;
+  g2.in = dense_view(gm, 4 * nb, P, K); g2.ones_row = -1;
+  g2.out = mk(a->gx);
+  g2.add = mk(a->gx);
+  if ((rc = launch_bgemm(g2, st))) return rc;
+
+  // 6. g(wm)[j, c] = sum gm[j] [x;1][c]
+  WgradParams w2;
+  w2.M = 4 * nb; w2.Cd = C1; w2.G = G; w2.P = P; w2.K = K;
+  w2.a = dense_view(gm, 4 * nb, P, K);
+  w2.b = mk(a->x);
+  w2.b_ones_row = Cin;
+  w2.partial = p_wm;
+  if ((rc = launch_wgrad(w2, st))) return rc;
+
+  // 7. reduce the split partials and scatter them into the parameter gradients
+  ReduceParams rp;
+  rp.nseg = 0;
+  auto seg = [&](const float* src, int S, long long sstride, int rows, int cols, int src_ld, float* dst, int dst_ld,
+                 const float* mul = nullptr, float* dst2 = nullptr) {
+    if (!dst && !dst2) return;
+    ReduceSeg& s = rp.seg[rp.nseg++];
+    s.src = src; s.S = S; s.sstride = sstride; s.rows = rows; s.cols = cols; s.src_ld = src_ld;
+    s.dst = dst; s.dst_ld = dst_ld; s.mul = mul; s.dst2 = dst2; s.scale = 1.0f;
+  };
+  const long long st_wcat = (long long)Cout * nb * C1, st_wm = (long long)4 * nb * C1;
+  const int P21 = 2 * P + 1;
+  for (int b = 0; b < nb; ++b) {
+    const dstd_branch_grad& g = a->gbr[b];
+    seg(p_wcat + b * C1, S1a, st_wcat, Cout, Cin, nb * C1, g.w_f, Cin);
+    seg(p_wcat + b * C1 + Cin, S1a, st_wcat, Cout, 1, nb * C1, g.b_f, 1);
+    seg(p_wm + (b * 4 + 0) * C1, S1a, st_wm, 2, Cin, C1, g.w_m1, Cin);
+    seg(p_wm + (b * 4 + 0) * C1 + Cin, S1a, st_wm, 2, 1, C1, g.b_m1, 1);
+    seg(p_wm + (b * 4 + 2) * C1, S1a, st_wm, 2, Cin, C1, g.w_m2, Cin);
+    seg(p_wm + (b * 4 + 2) * C1 + Cin, S1a, st_wm, 2, 1, C1, g.b_m2, 1);
+    seg(p_wrm + (long long)b * P * P21, S2, (long long)nb * P * P21, P, 2 * P, P21, g.w_rm, 2 * P);
+    seg(p_wrm + (long long)b * P * P21 + 2 * P, S2, (long long)nb * P * P21, P, 1, P21, g.b_rm, 1);
+    float* gadjw = a->br[b].adj_w ? g.adj_w : nullptr;
+    seg(p_adj + (long long)b * K * K, S2, (long long)nb * K * K, K, K, K, g.adj_eff, K, a->br[b].adj, gadjw);
+  }
+  seg(p_alpha, S2 * nb, 1, 1, 1, 1, a->alpha ? a->galpha : nullptr, 1);
+  return launch_reduce(rp, st);
+}
+
+// ---------------------------------------------------------------------------------------------- 1x1 channel mix
+extern "C" size_t dstd_chmix_bwd_workspace_bytes(int N, int Cin, int Cout, int P, int K) {
+  const long long G = (long long)N * P * K;
+  return arena_need({(size_t)wgrad_splits(G) * Cout * (Cin + 1) * 4});
+}
+
+extern "C" int dstd_chmix_forward(const dstd_chmix_fwd_args* a, dstd_stream_t stream) {
+  DSTD_REQUIRE(a && a->x.ptr && a->out.ptr && a->w, DSTD_ERR_BAD_ARG, "chmix_forward: null argument");
+  DSTD_REQUIRE(a->N > 0 && a->Cin > 0 && a->Cout > 0 && a->P > 0 && a->K > 0, DSTD_ERR_BAD_ARG,
+               "chmix_forward: non-positive dimension");
+  BgemmParams g;
+  g.M = a->Cout; g.Kd = a->Cin; g.G = (long long)a->N * a->P * a->K; g.P = a->P; g.K = a->K;
+  g.w = a->w; g.wsc = 1; g.wsi = a->Cin; g.bias = a->b;
+  g.in = mk(a->x); g.ones_row = -1;
+  g.out = mk(a->out);
+  g.add = View4{nullptr, 0, 0, 0, 0};
+  return launch_bgemm(g, (cudaStream_t)stream);
+}
+
+extern "C" int dstd_chmix_backward(const dstd_chmix_bwd_args* a, dstd_stream_t stream) {
+  DSTD_REQUIRE(a && a->x.ptr && a->gout.ptr && a->w, DSTD_ERR_BAD_ARG, "chmix_backward: null argument");
+  DSTD_REQUIRE(a->N > 0 && a->Cin > 0 && a->Cout > 0 && a->P > 0 && a->K > 0, DSTD_ERR_BAD_ARG,
+               "chmix_backward: non-positive dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cin = a->Cin, Cout = a->Cout, C1 = Cin + 1;
+  const long long G = (long long)a->N * a->P * a->K;
+  int rc;
+  if (a->gx.ptr) {
+    BgemmParams g;
+    g.M = Cin; g.Kd = Cout; g.G = G; g.P = a->P; g.K = a->K;
+    g.w = a->w; g.wsc = Cin; g.wsi = 1; g.bias = nullptr;
+    g.in = mk(a->gout); g.ones_row = -1;
+    g.out = mk(a->gx);
+    g.add = View4{nullptr, 0, 0, 0, 0};
+    if ((rc = launch_bgemm(g, st))) return rc;
+  }
+  if (a->gw || a->gb) {
+    DSTD_REQUIRE(a->ws && a->ws_bytes >= dstd_chmix_bwd_workspace_bytes(a->N, Cin, Cout, a->P, a->K),
+                 DSTD_ERR_WORKSPACE, "chmix_backward: workspace too small");
+    Arena ar(a->ws, a->ws_bytes);
+    const int S = wgrad_splits(G);
+    float* part = ar.take<float>((size_t)S * Cout * C1);
+    WgradParams w;
+    w.M = Cout; w.Cd = C1; w.G = G; w.P = a->P; w.K = a->K;
+    w.a = mk(a->gout);
+    w.b = mk(a->x);
+    w.b_ones_row = Cin;
+    w.partial = part;
+    if ((rc = launch_wgrad(w, st))) return rc;
+    const int Sa = w.S;
+    ReduceParams rp;
+    rp.nseg = 0;
+    if (a->gw) {
+      ReduceSeg& s = rp.seg[rp.nseg++];
+      s.src = part; s.S = Sa; s.sstride = (long long)Cout * C1; s.rows = Cout; s.cols = Cin; s.src_ld = C1;
+      s.dst = a->gw; s.dst_ld = Cin; s.mul = nullptr; s.dst2 = nullptr; s.scale = 1.0f;
+    }
+    if (a->gb) {
+      ReduceSeg& s = rp.seg[rp.nseg++];
+      s.src = part + Cin; s.S = Sa; s.sstride = (long long)Cout * C1; s.rows = Cout; s.cols = 1; s.src_ld = C1;
+      s.dst = a->gb; s.dst_ld = 1; s.mul = nullptr; s.dst2 = nullptr; s.scale = 1.0f;
+    }
+    return launch_reduce(rp, st);
+  }
+  return DSTD_OK;
+}

@@ -1,0 +1,99 @@
+// Shared device/host helpers for libdstd_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dstd_b200.h"
+
+namespace dstd {
+
+// ----------------------------------------------------------------------------- host side
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> status (+message)
+
+#define DSTD_REQUIRE(cond, code, ...)      \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::dstd::set_error(__VA_ARGS__);      \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+#define DSTD_LAUNCH_CHECK(what)                     \
+  do {                                              \
+    int _rc = ::dstd::check_launch(what);           \
+    if (_rc != 0) return _rc;                       \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t o = align_up(off, 256);
+    off = o + count * sizeof(T);
+    return (T*)(base + o);
+  }
+  bool ok() const { return off <= cap; }
+};
+static inline size_t arena_need(std::initializer_list<size_t> bytes) {
+  size_t o = 0;
+  for (size_t b : bytes) o = align_up(o, 256) + b;
+  return align_up(o, 256) + 256;
+}
+
+// ----------------------------------------------------------------------------- device side
+struct View4 {
+  float* p;
+  long long sn, sc, sp, sk;
+};
+static inline View4 mk(const dstd_view& v) { return View4{v.ptr, v.sn, v.sc, v.sp, v.sk}; }
+static inline View4 dense_view(float* p, long long C, long long P, long long K) {
+  return View4{p, C * P * K, P * K, K, 1};
+}
+
+__device__ __forceinline__ long long vix(const View4& v, int n, int c, int p, int k) {
+  return (long long)n * v.sn + (long long)c * v.sc + (long long)p * v.sp + (long long)k * v.sk;
+}
+
+// tanh with ~3e-7 absolute error: 1 - 2/(exp(2x)+1) through ex2.approx / rcp (two MUFU ops).
+// (tanh.approx.f32 is ~5e-4 relative: too coarse for the 1e-4 parity budget once scaled by conv_rm.)
+__device__ __forceinline__ float fast_tanh(float x) {
+  float e = exp2f(x * 2.885390081777927f);  // exp(2x); ex2.approx, saturates to inf / 0
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; `red` is >= 32 floats of shared memory; result valid in every thread
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  return r;
+}
+
+}  // namespace dstd

@@ -1,0 +1,342 @@
+// Dynamic adjacency construction of one DSTD-GC (model/dstdgcn.py:85-86 / :91-92) and its backward.
+//
+//   pd[p,v,w] = sum_{r,q} Wrm[p, r*P+q] * tanh(m1[r,q,v] - m2[r,q,w]) + brm[p]
+//
+// The pairwise tanh tensor D [2P,K,K] (135-216 KB/sample in the reference) never leaves the SM:
+//   forward : each thread owns NP (v,w) pairs and all P outputs (register tile), computes every tanh once in
+//             registers and streams Wrm^T rows from shared memory (broadcast float4 loads).
+//   backward: per sample, (v,w)-row chunks of D are rebuilt in shared memory and used by two register-blocked
+//             contractions: gWrm += gXm * D^T (accumulated in registers across the whole batch split) and
+//             gD = Wrm^T gXm -> gS = gD (1 - D^2) -> row/column sums give gm1 / gm2.
+#include "kernels.cuh"
+
+namespace dstd {
+
+// ================================================================================= forward
+template <int RT, int NP>
+__global__ void __launch_bounds__(256) dynadj_fwd_kernel(DynAdjFwdParams q) {
+  extern __shared__ __align__(16) float smem[];
+  const int P = q.P, K = q.K, PK = P * K, KK = K * K, P2 = 2 * P;
+  float* ms = smem;                       // [4][PK]
+  float* wT = ms + ((4 * PK + 3) & ~3);   // [2P][RT]
+  float* bs = wT + P2 * RT;               // [RT]
+  const int n = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* mg = q.m + ((long long)(n * q.nb + b) * 4) * PK;
+  const float* wrm = q.w_rm[b];
+  const float* brm = q.b_rm[b];
+  float* pdg = q.pd + (long long)(n * q.nb + b) * P * KK;
+
+  for (int i = tid; i < 4 * PK; i += blockDim.x) ms[i] = __ldg(mg + i);
+
+  const int items = (KK + NP - 1) / NP;
+  for (int p0 = 0; p0 < P; p0 += RT) {
+    __syncthreads();
+    for (int i = tid; i < P2 * RT; i += blockDim.x) {
+      int k = i / RT, pp = i - k * RT;
+      wT[i] = (p0 + pp < P) ? __ldg(wrm + (long long)(p0 + pp) * P2 + k) : 0.f;
+    }
+    for (int i = tid; i < RT; i += blockDim.x) bs[i] = (p0 + i < P) ? __ldg(brm + p0 + i) : 0.f;
+    __syncthreads();
+    for (int item = tid; item < items; item += blockDim.x) {
+      int vi[NP], wi[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        int e = item * NP + i;
+        if (e >= KK) e = KK - 1;
+        vi[i] = e / K;
+        wi[i] = e - vi[i] * K;
+      }
+      float acc[RT][NP];
+#pragma unroll
+      for (int pp = 0; pp < RT; ++pp)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc[pp][i] = bs[pp];
+#pragma unroll 2
+      for (int k = 0; k < P2; ++k) {
+        const int r = (k >= P) ? 1 : 0;
+        const float* m1 = ms + r * PK + (k - r * P) * K;
+        const float* m2 = m1 + 2 * PK;
+        float d[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) d[i] = fast_tanh(m1[vi[i]] - m2[wi[i]]);
+        const float4* w4 = reinterpret_cast<const float4*>(wT + k * RT);
+#pragma unroll
+        for (int p4 = 0; p4 < RT / 4; ++p4) {
+          float4 w = w4[p4];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            acc[p4 * 4 + 0][i] = fmaf(w.x, d[i], acc[p4 * 4 + 0][i]);
+            acc[p4 * 4 + 1][i] = fmaf(w.y, d[i], acc[p4 * 4 + 1][i]);
+            acc[p4 * 4 + 2][i] = fmaf(w.z, d[i], acc[p4 * 4 + 2][i]);
+            acc[p4 * 4 + 3][i] = fmaf(w.w, d[i], acc[p4 * 4 + 3][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int pp = 0; pp < RT; ++pp) {
+        if (p0 + pp < P) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            int e = item * NP + i;
+            if (e < KK) pdg[(long long)(p0 + pp) * KK + e] = acc[pp][i];
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int RT>
+static int dynadj_fwd_launch(const DynAdjFwdParams& q, cudaStream_t st) {
+  constexpr int NP = 2;
+  const int KK = q.K * q.K, PK = q.P * q.K;
+  int items = (KK + NP - 1) / NP;
+  int rounds = cdiv(items, 256);
+  int threads = cdiv(cdiv(items, rounds), 32) * 32;
+  size_t smem = ((size_t)((4 * PK + 3) & ~3) + (size_t)2 * q.P * RT + RT) * sizeof(float);
+  auto kern = dynadj_fwd_kernel<RT, NP>;
+  if (smem > 48 * 1024) {
+    DSTD_REQUIRE(smem <= 220 * 1024, DSTD_ERR_UNSUPPORTED, "dynadj_fwd: P=%d K=%d needs %zu B shared memory", q.P, q.K,
+                 smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  kern<<<dim3(q.N, q.nb), threads, smem, st>>>(q);
+  count_launch();
+  return check_launch("dynadj_fwd");
+}
+
+int launch_dynadj_fwd(const DynAdjFwdParams& q, cudaStream_t st) {
+  if (q.P <= 24) return dynadj_fwd_launch<24>(q, st);
+  if (q.P <= 28) return dynadj_fwd_launch<28>(q, st);
+  if (q.P <= 36) return dynadj_fwd_launch<36>(q, st);
+  return dynadj_fwd_launch<40>(q, st);   // P > 40: several register-tile passes (tanh recomputed per pass)
+}
+
+// ================================================================================= backward
+struct BwdGeom {
+  int RV, ECP, WLD;
+  size_t smem_floats;
+};
+static BwdGeom bwd_geom(int P, int K) {
+  BwdGeom g;
+  g.RV = 100 / K;
+  if (g.RV < 1) g.RV = 1;
+  if (g.RV > K) g.RV = K;
+  int ec = g.RV * K;
+  g.ECP = ec <= 36 ? 36 : ec <= 68 ? 68 : ec <= 100 ? 100 : ((ec + 31) / 32 * 32 + 4);
+  g.WLD = ((2 * P + 7) / 8) * 8;
+  size_t pk4 = (size_t)((4 * P * K + 3) & ~3);
+  g.smem_floats = 2 * pk4 + (size_t)P * g.ECP + (size_t)(2 * P + 1) * g.ECP + (size_t)P * g.WLD +
+                  (size_t)((K * K + 3) & ~3) + 32;
+  return g;
+}
+
+bool dynadj_supported(int P, int K) {
+  if (P > 40 || P < 1 || K < 1) return false;
+  return bwd_geom(P, K).smem_floats * sizeof(float) <= 220 * 1024;
+}
+
+int dynadj_bwd_splits(int N) { return N < 296 ? N : 296; }
+
+template <int TMA, int TNA>
+__global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int RV, int ECP, int WLD) {
+  extern __shared__ __align__(16) float smem[];
+  const int P = q.P, K = q.K, PK = P * K, KK = K * K, P2 = 2 * P;
+  const int pk4 = (4 * PK + 3) & ~3;
+  float* ms = smem;                    // [4][PK]
+  float* gms = ms + pk4;               // [4][PK]
+  float* gX = gms + pk4;               // [P][ECP]
+  float* Ds = gX + P * ECP;            // [2P+1][ECP]
+  float* Ws = Ds + (P2 + 1) * ECP;     // [P][WLD]
+  float* gA = Ws + P * WLD;            // [KK]
+  float* red = gA + ((KK + 3) & ~3);   // [32]
+
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+  const int b = blockIdx.y;
+  const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
+  const float* wrm = q.w_rm[b];
+
+  for (int i = tid; i < P * WLD; i += 256) {
+    int p = i / WLD, k = i - p * WLD;
+    Ws[i] = (k < P2) ? __ldg(wrm + (long long)p * P2 + k) : 0.f;
+  }
+  for (int i = tid; i < KK; i += 256) gA[i] = 0.f;
+
+  float accW[TMA][TNA];
+#pragma unroll
+  for (int a = 0; a < TMA; ++a)
+#pragma unroll
+    for (int c = 0; c < TNA; ++c) accW[a][c] = 0.f;
+  float galpha = 0.f;
+
+  // clamped row/column indices of this thread's gWrm tile
+  int prow[TMA], kcol[TNA];
+#pragma unroll
+  for (int a = 0; a < TMA; ++a) prow[a] = min(ty + 8 * a, P - 1);
+#pragma unroll
+  for (int c = 0; c < TNA; ++c) kcol[c] = min(lane + 32 * c, P2);
+
+  const int n_kt = (P2 + 7) / 8, n_et = ECP / 4;
+
+  for (int n = blockIdx.x; n < q.N; n += gridDim.x) {
+    const long long nb_ = (long long)n * q.nb + b;
+    const float* mg = q.m + nb_ * 4 * PK;
+    const float* gxm = q.gxm + nb_ * P * KK;
+    const float* pdg = q.pd + nb_ * P * KK;
+    __syncthreads();
+    for (int i = tid; i < 4 * PK; i += 256) {
+      ms[i] = __ldg(mg + i);
+      gms[i] = 0.f;
+    }
+    for (int v0 = 0; v0 < K; v0 += RV) {
+      const int rows = min(RV, K - v0), EC = rows * K, e0 = v0 * K;
+      __syncthreads();
+      // 1. stage gXm chunk (zero padded) ; galpha += gxm * pd
+      for (int i = tid; i < P * ECP; i += 256) {
+        int p = i / ECP, ec = i - p * ECP;
+        float g = 0.f;
+        if (ec < EC) {
+          long long o = (long long)p * KK + e0 + ec;
+          g = __ldg(gxm + o);
+          galpha = fmaf(g, __ldg(pdg + o), galpha);
+        }
+        gX[i] = g;
+      }
+      // 2. rebuild D chunk (+ ones row for the bias gradient)
+      for (int i = tid; i < (P2 + 1) * ECP; i += 256) {
+        int k = i / ECP, ec = i - k * ECP;
+        float d = 0.f;
+        if (ec < EC) {
+          if (k < P2) {
+            int r = (k >= P) ? 1 : 0, qq = k - r * P;
+            int vl = ec / K, w = ec - vl * K;
+            d = fast_tanh(ms[r * PK + qq * K + v0 + vl] - ms[(2 + r) * PK + qq * K + w]);
+          } else {
+            d = 1.0f;
+          }
+        }
+        Ds[i] = d;
+      }
+      __syncthreads();
+      // 3a. static-adjacency gradient: sum over p
+      if (tid < EC) {
+        float s = 0.f;
+        for (int p = 0; p < P; ++p) s += gX[p * ECP + tid];
+        gA[e0 + tid] += s;
+      }
+      // 3b. gWrm (+bias column) += gXm * D^T
+      for (int e4 = 0; e4 < ECP; e4 += 4) {
+        float4 g4[TMA], d4[TNA];
+#pragma unroll
+        for (int a = 0; a < TMA; ++a) g4[a] = *reinterpret_cast<const float4*>(gX + prow[a] * ECP + e4);
+#pragma unroll
+        for (int c = 0; c < TNA; ++c) d4[c] = *reinterpret_cast<const float4*>(Ds + kcol[c] * ECP + e4);
+#pragma unroll
+        for (int a = 0; a < TMA; ++a)
+#pragma unroll
+          for (int c = 0; c < TNA; ++c) {
+            accW[a][c] = fmaf(g4[a].x, d4[c].x, accW[a][c]);
+            accW[a][c] = fmaf(g4[a].y, d4[c].y, accW[a][c]);
+            accW[a][c] = fmaf(g4[a].z, d4[c].z, accW[a][c]);
+            accW[a][c] = fmaf(g4[a].w, d4[c].w, accW[a][c]);
+          }
+      }
+      __syncthreads();
+      // 4. gS = alpha * (Wrm^T gXm) * (1 - D^2), written over D
+      for (int tile = tid; tile < n_kt * n_et; tile += 256) {
+        int kt = tile / n_et, et = tile - kt * n_et;
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int p = 0; p < P; ++p) {
+          float4 w0 = *reinterpret_cast<const float4*>(Ws + p * WLD + kt * 8);
+          float4 w1 = *reinterpret_cast<const float4*>(Ws + p * WLD + kt * 8 + 4);
+          float4 g = *reinterpret_cast<const float4*>(gX + p * ECP + et * 4);
+          float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], gv[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int k = kt * 8 + i;
+          if (k < P2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              int ec = et * 4 + j;
+              float d = Ds[k * ECP + ec];
+              Ds[k * ECP + ec] = alpha * acc[i][j] * (1.0f - d * d);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // 5. gm1[k,v] = sum_w gS ; gm2[k,w] = -sum_v gS
+      for (int i = tid; i < P2 * rows; i += 256) {
+        int k = i / rows, vl = i - k * rows;
+        const float* row = Ds + k * ECP + vl * K;
+        float s = 0.f;
+        for (int w = 0; w < K; ++w) s += row[w];
+        int r = (k >= P) ? 1 : 0, qq = k - r * P;
+        gms[r * PK + qq * K + v0 + vl] += s;
+      }
+      for (int i = tid; i < P2 * K; i += 256) {
+        int k = i / K, w = i - k * K;
+        const float* col = Ds + k * ECP + w;
+        float s = 0.f;
+        for (int vl = 0; vl < rows; ++vl) s += col[vl * K];
+        int r = (k >= P) ? 1 : 0, qq = k - r * P;
+        gms[(2 + r) * PK + qq * K + w] -= s;
+      }
+    }
+    __syncthreads();
+    float* gmg = q.gm + nb_ * 4 * PK;
+    for (int i = tid; i < 4 * PK; i += 256) gmg[i] = gms[i];
+  }
+
+  // per-split partials
+  const long long sb = (long long)blockIdx.x * q.nb + b;
+  float* pw = q.part_wrm + sb * P * (P2 + 1);
+#pragma unroll
+  for (int a = 0; a < TMA; ++a) {
+    int p = ty + 8 * a;
+    if (p >= P) continue;
+#pragma unroll
+    for (int c = 0; c < TNA; ++c) {
+      int k = lane + 32 * c;
+      if (k <= P2) pw[p * (P2 + 1) + k] = alpha * accW[a][c];
+    }
+  }
+  __syncthreads();
+  float* pa = q.part_adj + sb * KK;
+  for (int i = tid; i < KK; i += 256) pa[i] = gA[i];
+  float ga = block_sum(galpha, red);
+  if (tid == 0) q.part_alpha[sb] = ga;
+}
+
+int launch_dynadj_bwd(const DynAdjBwdParams& q, cudaStream_t st) {
+  DSTD_REQUIRE(dynadj_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED,
+               "dynadj_bwd: P=%d K=%d outside the compiled tile limits (P<=40)", q.P, q.K);
+  BwdGeom g = bwd_geom(q.P, q.K);
+  size_t smem = g.smem_floats * sizeof(float);
+  int tma = cdiv(q.P, 8), tna = cdiv(2 * q.P + 1, 32);
+  dim3 grid(q.S, q.nb);
+#define DSTD_DYN_BWD(A, C)                                                                        \
+  {                                                                                               \
+    auto kern = dynadj_bwd_kernel<A, C>;                                                          \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    kern<<<grid, 256, smem, st>>>(q, g.RV, g.ECP, g.WLD);                                         \
+  }
+  if (tma <= 3 && tna <= 2) DSTD_DYN_BWD(3, 2)
+  else if (tma <= 4 && tna <= 2) DSTD_DYN_BWD(4, 2)
+  else DSTD_DYN_BWD(5, 3)
+#undef DSTD_DYN_BWD
+  count_launch();
+  return check_launch("dynadj_bwd");
+}
+
+}  // namespace dstd

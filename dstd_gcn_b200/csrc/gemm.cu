@@ -1,0 +1,278 @@
+// Generic channel-contraction kernels (fp32 SIMT, register-blocked, shared-memory staged):
+//   bgemm : Out[n,i,p,k] = sum_c W(c,i) In[n,c,p,k] (+ bias[i]) (+ Add[n,i,p,k])      "1x1 conv" family
+//   wgrad : G[i,c]       = sum_{n,p,k} A[n,i,p,k] B[n,c,p,k]                           weight gradients
+//   reduce_segments : sum split partials and scatter sub-matrices into parameter-gradient tensors
+// Columns g = (n,p,k) are flattened across the batch so tiles never straddle padding.
+#include "kernels.cuh"
+
+namespace dstd {
+
+// ================================================================================= bgemm
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) bgemm_kernel(BgemmParams q) {
+  constexpr int KC = 16;
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ __align__(16) float Ws[KC][BM];
+  __shared__ __align__(16) float Is[KC][BN];
+  __shared__ long long col_in[BN], col_out[BN], col_add[BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const long long g0 = (long long)blockIdx.x * BN;
+  const int row0 = q.m0 + blockIdx.y * BM;
+  const int PK = q.P * q.K;
+
+  for (int c = tid; c < BN; c += NT) {
+    long long g = g0 + c;
+    if (g < q.G) {
+      int n = (int)(g / PK);
+      int j = (int)(g - (long long)n * PK);
+      int p = j / q.K, k = j - p * q.K;
+      col_in[c] = vix(q.in, n, 0, p, k);
+      col_out[c] = vix(q.out, n, 0, p, k);
+      col_add[c] = q.add.p ? vix(q.add, n, 0, p, k) : 0;
+    } else {
+      col_in[c] = -1;
+      col_out[c] = -1;
+      col_add[c] = 0;
+    }
+  }
+  __syncthreads();
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+
+  for (int kc0 = 0; kc0 < q.Kd; kc0 += KC) {
+    for (int idx = tid; idx < KC * BM; idx += NT) {
+      int kk = idx / BM, i = idx - kk * BM;
+      int c = kc0 + kk, row = row0 + i;
+      float v = 0.f;
+      if (c < q.Kd && row < q.m1) v = __ldg(q.w + (long long)c * q.wsc + (long long)row * q.wsi);
+      Ws[kk][i] = v;
+    }
+    for (int idx = tid; idx < KC * BN; idx += NT) {
+      int kk = idx / BN, col = idx - kk * BN;
+      int c = kc0 + kk;
+      long long off = col_in[col];
+      float v = 0.f;
+      if (c < q.Kd && off >= 0) v = (c == q.ones_row) ? 1.0f : __ldg(q.in.p + off + (long long)c * q.in.sc);
+      Is[kk][col] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(&Ws[kk][ty * TM + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        float4 t = *reinterpret_cast<const float4*>(&Is[kk][tx * TN + j]);
+        b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int row = row0 + ty * TM + i;
+    if (row >= q.m1) continue;
+    float bv = q.bias ? __ldg(q.bias + row) : 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int col = tx * TN + j;
+      long long off = col_out[col];
+      if (off < 0) continue;
+      float v = acc[i][j] + bv;
+      if (q.add.p) v += q.add.p[col_add[col] + (long long)row * q.add.sc];
+      q.out.p[off + (long long)row * q.out.sc] = v;
+    }
+  }
+}
+
+int launch_bgemm(BgemmParams q, cudaStream_t st) {
+  if (q.G <= 0 || q.M <= 0) return 0;
+  // full 64-row tiles on the wide kernel, a remainder of <= 16 rows on the skinny one
+  int full = (q.M / 64) * 64;
+  int rem = q.M - full;
+  if (rem > 16) { full = q.M; rem = 0; }
+  if (full > 0) {
+    BgemmParams p = q;
+    p.m0 = 0;
+    p.m1 = full;
+    dim3 grid(cdiv(q.G, 128), cdiv(full, 64));
+    bgemm_kernel<64, 128, 8, 4><<<grid, 256, 0, st>>>(p);
+    count_launch();
+  }
+  if (rem > 0) {
+    BgemmParams p = q;
+    p.m0 = full;
+    p.m1 = q.M;
+    dim3 grid(cdiv(q.G, 256), 1);
+    bgemm_kernel<16, 256, 4, 4><<<grid, 256, 0, st>>>(p);
+    count_launch();
+  }
+  return check_launch("bgemm");
+}
+
+// ================================================================================= wgrad
+// G[i,c] = sum_g A[i,g] B[c,g].  Both operands are contiguous along the reduction index g, so tiles are staged
+// untransposed ([row][32 g] with a 36-float pitch: float4 reads along g are bank-conflict free for 32 lanes on
+// consecutive rows) and each thread owns rows {ty*TM+a} x columns {lane + 32 b}.
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradParams q) {
+  constexpr int KC = 32, PITCH = 36;
+  constexpr int BM = 8 * TM, BC = 32 * TN;
+  __shared__ __align__(16) float As[BM][PITCH];
+  __shared__ __align__(16) float Bs[BC][PITCH];
+  __shared__ long long a_off[KC], b_off[KC];
+
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+  const int i0 = blockIdx.y * BM, c0 = blockIdx.z * BC;
+  const int PK = q.P * q.K;
+  long long gbeg = (long long)blockIdx.x * q.cols_per_split;
+  long long gend = gbeg + q.cols_per_split;
+  if (gend > q.G) gend = q.G;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+
+  for (long long gc = gbeg; gc < gend; gc += KC) {
+    if (tid < KC) {
+      long long g = gc + tid;
+      if (g < gend) {
+        int n = (int)(g / PK);
+        int j = (int)(g - (long long)n * PK);
+        int p = j / q.K, k = j - p * q.K;
+        a_off[tid] = vix(q.a, n, 0, p, k);
+        b_off[tid] = vix(q.b, n, 0, p, k);
+      } else {
+        a_off[tid] = -1;
+        b_off[tid] = -1;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < BM * KC; idx += 256) {
+      int i = idx >> 5, kk = idx & 31;
+      long long off = a_off[kk];
+      float v = 0.f;
+      if (off >= 0 && i0 + i < q.M) v = __ldg(q.a.p + off + (long long)(i0 + i) * q.a.sc);
+      As[i][kk] = v;
+    }
+    for (int idx = tid; idx < BC * KC; idx += 256) {
+      int c = idx >> 5, kk = idx & 31;
+      long long off = b_off[kk];
+      int cc = c0 + c;
+      float v = 0.f;
+      if (off >= 0 && cc < q.Cd) v = (cc == q.b_ones_row) ? 1.0f : __ldg(q.b.p + off + (long long)cc * q.b.sc);
+      Bs[c][kk] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      float4 a4[TM], b4[TN];
+#pragma unroll
+      for (int a = 0; a < TM; ++a) a4[a] = *reinterpret_cast<const float4*>(&As[ty * TM + a][k4]);
+#pragma unroll
+      for (int b = 0; b < TN; ++b) b4[b] = *reinterpret_cast<const float4*>(&Bs[lane + 32 * b][k4]);
+#pragma unroll
+      for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) {
+          acc[a][b] = fmaf(a4[a].x, b4[b].x, acc[a][b]);
+          acc[a][b] = fmaf(a4[a].y, b4[b].y, acc[a][b]);
+          acc[a][b] = fmaf(a4[a].z, b4[b].z, acc[a][b]);
+          acc[a][b] = fmaf(a4[a].w, b4[b].w, acc[a][b]);
+        }
+    }
+    __syncthreads();
+  }
+  float* dst = q.partial + (long long)blockIdx.x * q.M * q.Cd;
+#pragma unroll
+  for (int a = 0; a < TM; ++a) {
+    int i = i0 + ty * TM + a;
+    if (i >= q.M) continue;
+#pragma unroll
+    for (int b = 0; b < TN; ++b) {
+      int c = c0 + lane + 32 * b;
+      if (c < q.Cd) dst[(long long)i * q.Cd + c] = acc[a][b];
+    }
+  }
+}
+
+int wgrad_splits(long long G) {
+  long long s = (G + 2047) / 2048;
+  if (s > 296) s = 296;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+template <int TM>
+static void wgrad_dispatch_tn(const WgradParams& q, int tn, dim3 grid, cudaStream_t st) {
+  switch (tn) {
+    case 1: wgrad_kernel<TM, 1><<<grid, 256, 0, st>>>(q); break;
+    case 2: wgrad_kernel<TM, 2><<<grid, 256, 0, st>>>(q); break;
+    case 3: wgrad_kernel<TM, 3><<<grid, 256, 0, st>>>(q); break;
+    case 4: wgrad_kernel<TM, 4><<<grid, 256, 0, st>>>(q); break;
+    default: wgrad_kernel<TM, 5><<<grid, 256, 0, st>>>(q); break;
+  }
+}
+
+// partial must hold wgrad_splits(G) * M * Cd floats
+int launch_wgrad(WgradParams& q, cudaStream_t st) {
+  q.S = wgrad_splits(q.G);
+  long long per = (q.G + q.S - 1) / q.S;
+  q.cols_per_split = (per + 31) / 32 * 32;
+  q.S = cdiv(q.G, q.cols_per_split);
+  int tn = cdiv(q.Cd, 32);
+  if (tn > 5) tn = (q.Cd % 128 == 0 || q.Cd > 160) ? 4 : 5;
+  if (q.M <= 8) {
+    dim3 grid(q.S, cdiv(q.M, 8), cdiv(q.Cd, 32 * tn));
+    wgrad_dispatch_tn<1>(q, tn, grid, st);
+  } else {
+    dim3 grid(q.S, cdiv(q.M, 64), cdiv(q.Cd, 32 * tn));
+    wgrad_dispatch_tn<8>(q, tn, grid, st);
+  }
+  count_launch();
+  return check_launch("wgrad");
+}
+
+// ================================================================================= reduce + scatter
+__global__ void reduce_segments_kernel(ReduceParams q) {
+  const ReduceSeg& s = q.seg[blockIdx.y];
+  int total = s.rows * s.cols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int r = idx / s.cols, c = idx - r * s.cols;
+    const float* src = s.src + (long long)r * s.src_ld + c;
+    float v = 0.f;
+    for (int k = 0; k < s.S; ++k) v += src[(long long)k * s.sstride];
+    v *= s.scale;
+    if (s.dst) s.dst[(long long)r * s.dst_ld + c] = v;
+    if (s.dst2) s.dst2[(long long)r * s.dst_ld + c] = v * __ldg(s.mul + (long long)r * s.dst_ld + c);
+  }
+}
+
+int launch_reduce(const ReduceParams& q, cudaStream_t st) {
+  if (q.nseg == 0) return 0;
+  int maxe = 1;
+  for (int i = 0; i < q.nseg; ++i) maxe = max(maxe, q.seg[i].rows * q.seg[i].cols);
+  dim3 grid(min(cdiv(maxe, 128), 64), q.nseg);
+  reduce_segments_kernel<<<grid, 128, 0, st>>>(q);
+  count_launch();
+  return check_launch("reduce_segments");
+}
+
+}  // namespace dstd

@@ -1,0 +1,119 @@
+// Internal launcher interface between api.cu and the kernel translation units.
+#pragma once
+#include <initializer_list>
+
+#include "common.cuh"
+
+namespace dstd {
+
+// ------------------------------------------------------------------ gemm.cu
+struct BgemmParams {
+  int M, Kd;           // output rows, reduction length
+  long long G;         // columns = N*P*K
+  int P, K;
+  const float* w;      // weight element (c, i) at w[c*wsc + i*wsi]
+  long long wsc, wsi;
+  const float* bias;   // [M] or null
+  View4 in;            // row c at in.p + c*in.sc
+  int ones_row;        // row index that reads as 1.0 (or -1)
+  View4 out;
+  View4 add;           // optional (p == null)
+  int m0, m1;          // filled by the launcher
+};
+int launch_bgemm(BgemmParams q, cudaStream_t st);
+
+struct WgradParams {
+  int M, Cd;
+  long long G;
+  int P, K;
+  View4 a;             // [*, M, P, K]
+  View4 b;             // [*, Cd, P, K]
+  int b_ones_row;      // row of B that reads as 1.0 (or -1)
+  float* partial;      // [S][M][Cd]
+  int S;               // filled by the launcher
+  long long cols_per_split;
+};
+int wgrad_splits(long long G);
+int launch_wgrad(WgradParams& q, cudaStream_t st);   // fills q.S (number of partials actually written)
+
+struct ReduceSeg {
+  const float* src;    // partial k, element (r, c) at src[k*sstride + r*src_ld + c]
+  int S;
+  long long sstride;
+  int rows, cols, src_ld;
+  float* dst;          // dense [rows][dst_ld]; may be null
+  int dst_ld;
+  const float* mul;    // optional: dst2 = value * mul (same indexing as dst)
+  float* dst2;
+  float scale;
+};
+struct ReduceParams {
+  ReduceSeg seg[24];
+  int nseg;
+};
+int launch_reduce(const ReduceParams& q, cudaStream_t st);
+
+// ------------------------------------------------------------------ dynadj.cu
+struct DynAdjFwdParams {
+  int N, P, K, nb;
+  const float* m;      // [N,nb,4,P,K]
+  const float* w_rm[DSTD_MAX_BRANCH];
+  const float* b_rm[DSTD_MAX_BRANCH];
+  float* pd;           // [N,nb,P,K,K]
+};
+int launch_dynadj_fwd(const DynAdjFwdParams& q, cudaStream_t st);
+
+struct DynAdjBwdParams {
+  int N, P, K, nb;
+  const float* m;      // [N,nb,4,P,K]
+  const float* pd;     // [N,nb,P,K,K]
+  const float* gxm;    // [N,nb,P,K,K]
+  const float* w_rm[DSTD_MAX_BRANCH];
+  const float* alpha;  // device scalar or null (=1)
+  float* gm;           // [N,nb,4,P,K]
+  int S;               // number of batch splits
+  float* part_wrm;     // [S][nb][P][2P+1]   (already scaled by alpha)
+  float* part_adj;     // [S][nb][K*K]
+  float* part_alpha;   // [S][nb]
+};
+int dynadj_bwd_splits(int N);
+int launch_dynadj_bwd(const DynAdjBwdParams& q, cudaStream_t st);
+bool dynadj_supported(int P, int K);
+
+// ------------------------------------------------------------------ aggregate.cu
+struct AggParams {
+  int N, Cin, P, K, nb, adj_t;
+  View4 x;             // [N,Cin,P,K]
+  const float* pd;     // [N,nb,P,K,K]
+  const float* alpha;
+  const float* adj[DSTD_MAX_BRANCH];
+  const float* adj_w[DSTD_MAX_BRANCH];
+  const float* adj_r[DSTD_MAX_BRANCH];
+  float* xa;           // fwd out: [N,nb,Cin+1,P,K]
+  // backward only
+  const float* gxa;    // [N,nb,Cin+1,P,K]
+  View4 gx;            // [N,Cin,P,K] written
+  float* gxm;          // [N,nb,P,K,K] written
+};
+int launch_aggregate_fwd(const AggParams& q, cudaStream_t st);
+int launch_aggregate_bwd(const AggParams& q, cudaStream_t st);
+bool aggregate_supported(int Cin, int P, int K);
+
+// ------------------------------------------------------------------ bn_act.cu
+int bn_act_splits(int N);
+
+// ------------------------------------------------------------------ misc.cu
+struct PackParams {
+  int Cin, Cout, nb;
+  const float* w_f[DSTD_MAX_BRANCH];
+  const float* b_f[DSTD_MAX_BRANCH];
+  const float* w_m1[DSTD_MAX_BRANCH];
+  const float* b_m1[DSTD_MAX_BRANCH];
+  const float* w_m2[DSTD_MAX_BRANCH];
+  const float* b_m2[DSTD_MAX_BRANCH];
+  float* wcat;         // [Cout][nb*(Cin+1)]
+  float* wm;           // [4*nb][Cin+1]
+};
+int launch_pack(const PackParams& q, cudaStream_t st);
+
+}  // namespace dstd

@@ -1,0 +1,113 @@
+"""Training / evaluation step glue, the device-side counterpart of ``PredictionEngine.train`` / ``.test``
+(/root/reference/engine/prediction.py:198-317, :319-430) for the DSTD-GCN hot path.
+
+One ``TrainStep`` call is one iteration of the reference loop body (:215-294):
+
+    outputs = model(tsc(inputs));            loss  = mpjpe(outputs, targets)             (:231-258)
+    outputs = model(tsc(inputs_inv));        loss += mpjpe(outputs, targets[:, ::-1])    (:267-287)   if inverse
+    loss /= 2;  zero_grad;  loss.backward();  [clip];  optimizer.step()                  (:287-294)
+
+with the differences that make it a B200 data-parallel step:
+  * trainable parameters, their gradients and the Adam moments live in flat fp32 buckets (the module's parameters are
+    views into the bucket, so ``state_dict()`` / checkpoints are unchanged);
+  * the batch is sharded over ranks; the only collective is one ``all_reduce(sum)`` of the flat gradient bucket
+    (NCCL over NVLink), with the 1/world scaling folded into the fused Adam kernel;
+  * the loss and its gradient come out of one kernel and the loss stays on the device (no per-step ``.item()`` sync,
+    cf. prediction.py:264).
+BatchNorm statistics are per rank (DDP-without-SyncBN semantics).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class FlatParams:
+    """Re-homes a module's trainable parameters into one contiguous fp32 bucket (and a matching gradient bucket)."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+        total = sum(p.numel() for _, p in self.named)
+        dev = self.named[0][1].device
+        self.param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slices = {}
+        off = 0
+        for k, p in self.named:
+            n = p.numel()
+            self.param[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.param[off:off + n].view(p.shape)
+            p.grad = self.grad[off:off + n].view(p.shape)
+            self.slices[k] = (off, n, tuple(p.shape))
+            off += n
+        self.numel = total
+
+    def rebind_grads(self):
+        """autograd accumulates in place into the views; re-attach them if something detached a ``.grad``."""
+        for k, p in self.named:
+            off, n, shape = self.slices[k]
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                p.grad = self.grad[off:off + n].view(shape)
+
+
+class TrainStep:
+    """One optimisation step of the reference engine loop on the sm_100a kernels.
+
+    ``inputs``, ``inputs_inv``, ``targets``: raw ``[N, T, 3V]`` fp32 batches already on the device (this rank's shard).
+    Returns the (device, 0-dim) loss of this rank's shard.
+    """
+
+    def __init__(self, model, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, inverse=True, clip=-1.0,
+                 process_group: Optional[dist.ProcessGroup] = None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.inverse, self.clip = bool(inverse), float(clip)
+        self.flat = FlatParams(model)
+        self.exp_avg = torch.zeros_like(self.flat.param)
+        self.exp_avg_sq = torch.zeros_like(self.flat.param)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+
+    def grad_of(self, name):
+        off, n, shape = self.flat.slices[name]
+        return self.flat.grad[off:off + n].view(shape)
+
+    def loss_and_grads(self, inputs, inputs_inv, targets):
+        n, t, vc = inputs.shape
+        v = vc // 3
+        scale = 0.5 if self.inverse else 1.0
+        self.flat.rebind_grads()
+        self.flat.grad.zero_()
+        out = self.model(inputs.view(n, t, v, 3))
+        loss = ops.mpjpe(out.reshape(n, t, vc), targets, scale)
+        if self.inverse:
+            out_i = self.model(inputs_inv.view(n, t, v, 3))
+            loss = loss + ops.mpjpe(out_i.reshape(n, t, vc), torch.flip(targets, dims=[1]), scale)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, inputs, inputs_inv, targets):
+        loss = self.loss_and_grads(inputs, inputs_inv, targets)
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        gscale = 1.0 / self.world
+        if self.clip > 0:
+            gn = torch.linalg.vector_norm(self.flat.grad) * gscale
+            self.flat.grad.mul_(torch.clamp(self.clip / (gn + 1e-6), max=1.0))
+        self.step_count += 1
+        torch.ops.dstd_b200.adam_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr,
+                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, gscale,
+                                      self.step_count)
+        return loss
+
+
+@torch.no_grad()
+def predict(model, inputs):
+    """Eval-mode forward on raw ``[N, T, 3V]`` batches (engine/prediction.py:340-353)."""
+    n, t, vc = inputs.shape
+    return model(inputs.view(n, t, vc // 3, 3)).reshape(n, t, vc)

@@ -67,7 +67,8 @@ typedef struct {
 /* gradients of the above; any pointer may be NULL (not wanted).  Written, not accumulated. */
 typedef struct {
   float *w_m1, *b_m1, *w_m2, *b_m2, *w_rm, *b_rm, *w_f, *b_f;
-  float *adj_eff; /* d/d(adj*adj_w + adj_r) [K,K]; caller derives dW_s = A_s*g, dR_s = g (dstdgcn.py:149,160) */
+  float *adj_eff; /* d/d(adj*adj_w + adj_r) [K,K]  (= dR_s / dR_t; fast variant: dA_s)  (dstdgcn.py:149,160) */
+  float *adj_w;   /* d/d adj_w = adj * adj_eff [K,K] (dW_s); only written when the branch has adj_w */
 } dstd_branch_grad;
 
 /* ---------------------------------------------------------------------------------------------

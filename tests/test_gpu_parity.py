@@ -1,0 +1,411 @@
+"""GPU parity tests proper: every C-ABI entry point of libdstd_b200 (called through ctypes) against the ABI
+emulation / oracle in float64 on the same seeded inputs, then modules, whole models and training steps against the
+reference golden fixtures.  Tolerances (fp32 kernels vs fp64 truth): forward max-abs 1e-4 at unit scale, gradients
+relative 1e-4, looser only where stated."""
+import pytest
+import torch
+
+import dstd_gcn_b200  # noqa: F401
+from dstd_gcn_b200 import _lib
+from oracle.abi_emul import EmulBackend
+from tests.helpers import load_npz, max_abs, rel_err, split
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+EM = EmulBackend()
+
+
+def cuda_backend():
+    b = _lib.backend()
+    assert b.name == "cuda"
+    return b
+
+
+def rnd(shape, gen, scale=1.0):
+    return torch.randn(shape, generator=gen, dtype=torch.float64) * scale
+
+
+def to_dev(t):
+    if t is None:
+        return None
+    out = torch.empty_strided(t.shape, t.stride(), dtype=torch.float32, device=DEV)
+    out.copy_(t.float())
+    return out
+
+
+def make_branches(g, nb, cin, cout, p, k, with_w=True, with_r=True):
+    brs = []
+    for _ in range(nb):
+        br = dict(w_m1=rnd((2, cin, 1, 1), g, 0.3), b_m1=rnd((2,), g, 0.1), w_m2=rnd((2, cin, 1, 1), g, 0.3),
+                  b_m2=rnd((2,), g, 0.1), w_rm=rnd((p, 2 * p, 1, 1), g, 0.2), b_rm=rnd((p,), g, 0.1),
+                  w_f=rnd((cout, cin, 1, 1), g, 0.3), b_f=rnd((cout,), g, 0.1),
+                  adj=(torch.rand((k, k), generator=g, dtype=torch.float64) > 0.7).double(),
+                  adj_w=rnd((k, k), g, 0.2) if with_w else None, adj_r=rnd((k, k), g, 0.2) if with_r else None)
+        brs.append(br)
+    return brs
+
+
+def dev_branches(brs):
+    return [{k: to_dev(v) for k, v in br.items()} for br in brs]
+
+
+def unit_input(g, n, c, p, k, layout):
+    """[N,C,P,K] logical tensor in one of the memory orders the modules produce."""
+    if layout == "pk":        # contiguous (spatial unit on [N,C,T,V])
+        return rnd((n, c, p, k), g)
+    if layout == "kp":        # K-major memory (temporal unit viewed from [N,C,T,V])
+        return rnd((n, c, k, p), g).permute(0, 1, 3, 2)
+    if layout == "cl_pk":     # channels-last (fast variant's public layout), spatial unit
+        return rnd((n, p, k, c), g).permute(0, 3, 1, 2)
+    raise ValueError(layout)
+
+
+GC_CASES = [
+    # n, cin, cout, p, k, nb, layout, adj_t, skip
+    (3, 6, 16, 35, 22, 2, "pk", False, False),     # input block, spatial, H3.6M
+    (2, 16, 16, 22, 35, 1, "pk", False, True),     # temporal unit with layer skip
+    (2, 64, 64, 35, 22, 2, "pk", False, False),    # encoder spatial, full width
+    (2, 64, 64, 22, 35, 1, "kp", False, True),     # temporal unit on a transposed view
+    (2, 16, 3, 40, 23, 2, "pk", False, False),     # output block, 3DPW
+    (2, 3, 3, 25, 35, 1, "pk", False, False),      # output block temporal (3 -> 3), CMU
+    (2, 8, 8, 12, 22, 2, "cl_pk", True, False),    # fast variant: transposed adjacency, channels-last
+    (1, 5, 7, 3, 4, 1, "pk", True, True),          # tiny / ragged
+    (5, 64, 64, 40, 23, 2, "pk", False, False),    # 3DPW encoder
+]
+
+
+@pytest.mark.parametrize("case", GC_CASES, ids=[str(i) for i in range(len(GC_CASES))])
+def test_gc_unit_abi(case):
+    n, cin, cout, p, k, nb, layout, adj_t, use_skip = case
+    g = torch.Generator().manual_seed(100 + cin * 7 + p)
+    be = cuda_backend()
+    x = unit_input(g, n, cin, p, k, layout)
+    skip = unit_input(g, n, cout, p, k, layout) if use_skip else None
+    alpha = rnd((1,), g, 0.3) + 0.5
+    brs = make_branches(g, nb, cin, cout, p, k, with_w=(nb == 2), with_r=True)
+    out_r, m_r, pd_r, xa_r = EM.gc_forward(x, alpha, brs, skip, adj_t)
+    xd, sd, ad, bd = to_dev(x), to_dev(skip), to_dev(alpha), dev_branches(brs)
+    out, m, pd, xa = be.gc_forward(xd, ad, bd, sd, adj_t)
+    torch.cuda.synchronize()
+    assert out.stride() == out_r.stride()
+    assert max_abs(m, m_r) < 2e-5
+    assert max_abs(pd, pd_r) < 5e-5
+    assert max_abs(xa, xa_r) < 1e-4 * max(1.0, float(xa_r.abs().max()) / 10)
+    assert max_abs(out, out_r) < 1e-4 * max(1.0, float(out_r.abs().max()) / 10)
+
+    gout = unit_input(g, n, cout, p, k, layout)
+    gx_r, ga_r, gr_r = EM.gc_backward(x, gout, alpha, brs, m_r, pd_r, xa_r, adj_t)
+    gx, ga, gr = be.gc_backward(xd, to_dev(gout), ad, bd, m, pd, xa, adj_t)
+    torch.cuda.synchronize()
+    assert gx.stride() == xd.stride()
+    assert rel_err(gx, gx_r) < 1e-4
+    assert rel_err(ga, ga_r) < 1e-4
+    for b in range(nb):
+        for key, ref in gr_r[b].items():
+            if ref is None:
+                assert gr[b][key] is None
+                continue
+            assert gr[b][key].shape == ref.shape, key
+            assert max_abs(gr[b][key], ref) < 1e-4 * max(1.0, float(ref.abs().max())), (b, key)
+
+
+def test_gc_unit_errors():
+    be = cuda_backend()
+    g = torch.Generator().manual_seed(5)
+    x = to_dev(rnd((1, 4, 50, 8), g))
+    brs = dev_branches(make_branches(g, 1, 4, 4, 50, 8))
+    with pytest.raises(RuntimeError, match="tile limits"):
+        be.gc_forward(x, None, brs, None, False)          # P > 40: outside the compiled limits -> loud error
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        be.gc_forward(x.cpu(), None, brs, None, False)     # no CPU fallback
+
+
+BN_CASES = [
+    # n, c, t, v, y_order, r_order, out_order, vc, prelu, mask, training
+    (4, 16, 35, 22, "t", "t", 2, False, True, False, True),    # block BN: T-major in, V-major out, residual
+    (4, 16, 35, 22, "v", None, 1, False, True, True, True),    # bn_in / encoder BN: V-major in, T-major out, dropout mask
+    (3, 8, 10, 25, "t", None, 0, True, False, False, True),    # plain BatchNorm module, fast channel order
+    (3, 8, 40, 23, "v", "v", 0, False, True, False, False),    # eval mode
+    (40, 64, 35, 22, "v", None, 1, False, True, False, True),  # more samples than splits
+    (2, 3, 35, 22, "t", "t", 2, False, True, False, True),     # output block (3 channels)
+]
+
+
+def _ordered(g, n, c, t, v, order):
+    if order == "t":
+        return rnd((n, c, t, v), g)
+    return rnd((n, c, v, t), g).permute(0, 1, 3, 2)
+
+
+@pytest.mark.parametrize("case", BN_CASES, ids=[str(i) for i in range(len(BN_CASES))])
+def test_bn_act_abi(case):
+    n, c, t, v, yo, ro, out_order, vc, use_prelu, use_mask, training = case
+    g = torch.Generator().manual_seed(n * 13 + c)
+    be = cuda_backend()
+    y = _ordered(g, n, c, t, v, yo) * 2.0 + 3.0
+    r = _ordered(g, n, c, t, v, ro) if ro else None
+    gamma, beta = rnd((c * v,), g, 0.5) + 1.0, rnd((c * v,), g, 0.5)
+    rm, rv = rnd((c * v,), g, 0.5), torch.rand((c * v,), generator=g, dtype=torch.float64) + 0.5
+    nbt = torch.tensor(3, dtype=torch.int64)
+    prelu = torch.tensor([0.25], dtype=torch.float64) if use_prelu else None
+    mask = ((torch.rand((n, c, t, v), generator=g) > 0.1).double() / 0.9) if use_mask else None
+    from dstd_gcn_b200.ops import _out_like
+    ol = _out_like(y, out_order)
+    rm_r, rv_r, nbt_r = rm.clone(), rv.clone(), nbt.clone()
+    out_r, mean_r, istd_r = EM.bn_act_forward(y, r, gamma, beta, rm_r, rv_r, nbt_r, prelu, mask, vc, training, 1e-5,
+                                              0.1, ol if out_order else None)
+    yd, rd = to_dev(y), to_dev(r)
+    gd, bd, rmd, rvd, nbd = to_dev(gamma), to_dev(beta), to_dev(rm), to_dev(rv), nbt.to(DEV)
+    pd_, md = to_dev(prelu), to_dev(mask)
+    old = _out_like(yd, out_order)
+    out, mean, istd = be.bn_act_forward(yd, rd, gd, bd, rmd, rvd, nbd if training else None, pd_, md, vc, training,
+                                        1e-5, 0.1, old if out_order else None)
+    torch.cuda.synchronize()
+    assert out.stride() == out_r.stride()
+    assert max_abs(out, out_r) < 2e-5 * max(1.0, float(out_r.abs().max()))
+    assert max_abs(mean, mean_r) < 1e-5 and rel_err(istd, istd_r) < 1e-5
+    if training:
+        assert max_abs(rmd, rm_r) < 1e-5 and max_abs(rvd, rv_r) < 1e-5 and int(nbd) == int(nbt_r)
+    gout = torch.empty_strided(out_r.shape, out_r.stride(), dtype=torch.float64)
+    gout.copy_(rnd(tuple(out_r.shape), g))
+    res_r = EM.bn_act_backward(y, r, gout, gamma, beta, prelu, mask, mean_r, istd_r, vc, training, True)
+    res = be.bn_act_backward(yd, rd, to_dev(gout), gd, bd, pd_, md, mean, istd, vc, training, True)
+    torch.cuda.synchronize()
+    names = ("gy", "gr", "ggamma", "gbeta", "gprelu")
+    for nm, a, b in zip(names, res, res_r):
+        if b is None:
+            assert a is None, nm
+            continue
+        assert a.shape == b.shape, nm
+        assert max_abs(a, b) < 1e-4 * max(1.0, float(b.abs().max())), nm
+
+
+def test_bn_act_large_mean_is_stable():
+    """millimetre-scale activations (mean >> std): shifted sums keep the variance accurate."""
+    be = cuda_backend()
+    g = torch.Generator().manual_seed(3)
+    n, c, t, v = 32, 4, 35, 22
+    y = rnd((n, c, t, v), g) * 0.5 + 3000.0
+    gamma, beta = torch.ones(c * v, dtype=torch.float64), torch.zeros(c * v, dtype=torch.float64)
+    out_r, _, istd_r = EM.bn_act_forward(y, None, gamma, beta, None, None, None, None, None, False, True, 1e-5, 0.1)
+    out, _, istd = be.bn_act_forward(to_dev(y), None, to_dev(gamma), to_dev(beta), None, None, None, None, None, False,
+                                     True, 1e-5, 0.1)
+    assert rel_err(istd, istd_r) < 1e-3       # the fp32 inputs themselves are only good to 3000 * 6e-8 = 2e-4
+    assert max_abs(out, out_r) < 5e-3
+
+
+@pytest.mark.parametrize("layout", ["pk", "kp", "cl_pk"])
+def test_chmix_abi(layout):
+    be = cuda_backend()
+    g = torch.Generator().manual_seed(11)
+    n, cin, cout, p, k = 3, 6, 64, 35, 22
+    x = unit_input(g, n, cin, p, k, layout)
+    w, b = rnd((cout, cin), g, 0.3), rnd((cout,), g, 0.1)
+    o_r = EM.chmix_forward(x, w, b)
+    o = be.chmix_forward(to_dev(x), to_dev(w), to_dev(b))
+    assert o.stride() == o_r.stride() and max_abs(o, o_r) < 1e-5
+    go = unit_input(g, n, cout, p, k, layout)
+    gx_r, gw_r, gb_r = EM.chmix_backward(x, go, w, True)
+    gx, gw, gb = be.chmix_backward(to_dev(x), to_dev(go), to_dev(w), True)
+    assert max_abs(gx, gx_r) < 1e-4 and rel_err(gw, gw_r) < 1e-5 and rel_err(gb, gb_r) < 1e-5
+
+
+def test_head_tail_loss_adam_abi():
+    be = cuda_backend()
+    g = torch.Generator().manual_seed(21)
+    n, t, v = 5, 35, 22
+    x = rnd((n, t, v, 3), g)
+    h_r = EM.prep_forward(x)
+    h = be.prep_forward(to_dev(x))
+    assert max_abs(h, h_r) < 1e-6
+    gh = rnd((n, 6, t, v), g)
+    assert max_abs(be.prep_backward(to_dev(gh)), EM.prep_backward(gh)) < 1e-5
+    z = rnd((n, 3, v, t), g).permute(0, 1, 3, 2)
+    assert max_abs(be.finish_forward(to_dev(z), to_dev(x)), EM.finish_forward(z, x)) < 1e-6
+    gy = rnd((n, t, v, 3), g)
+    gz, gx = be.finish_backward(to_dev(gy), True)
+    gz_r, gx_r = EM.finish_backward(gy, True)
+    assert max_abs(gz, gz_r) < 1e-6 and max_abs(gx, gx_r) < 1e-5
+    # mpjpe
+    pred, tgt = rnd((n, t, v * 3), g), rnd((n, t, v * 3), g)
+    l_r = torch.zeros((), dtype=torch.float64)
+    gp_r = EM.mpjpe(pred, tgt, 0.5, l_r, False)
+    l = torch.zeros((), dtype=torch.float32, device=DEV)
+    gp = be.mpjpe(to_dev(pred), to_dev(tgt), 0.5, l, False)
+    assert abs(float(l) - float(l_r)) < 1e-6 and max_abs(gp, gp_r) < 1e-8
+    be.mpjpe(to_dev(pred), to_dev(tgt), 0.5, l, True)
+    assert abs(float(l) - 2 * float(l_r)) < 1e-6
+    # adam
+    nprm = 10007
+    p0, gr = rnd((nprm,), g), rnd((nprm,), g)
+    m0, v0 = rnd((nprm,), g, 0.1), torch.rand((nprm,), generator=g, dtype=torch.float64) * 0.01
+    pr, mr, vr = p0.clone(), m0.clone(), v0.clone()
+    EM.adam_step(pr, gr, mr, vr, 3e-3, 0.9, 0.999, 1e-8, 0.0, 0.5, 7)
+    pd_, md, vd = to_dev(p0), to_dev(m0), to_dev(v0)
+    be.adam_step(pd_, to_dev(gr), md, vd, 3e-3, 0.9, 0.999, 1e-8, 0.0, 0.5, 7)
+    assert max_abs(pd_, pr) < 1e-6 and max_abs(md, mr) < 1e-6 and max_abs(vd, vr) < 1e-7
+
+
+# ================================================================================================= modules vs goldens
+def _mod(variant):
+    from dstd_gcn_b200.model import dstdgcn as std
+    from dstd_gcn_b200.model import dstdgcn_fast as fast
+    return std if variant == "std" else fast
+
+
+def _load(module, params):
+    sd = module.state_dict()
+    for k in sd:
+        sd[k] = params[k].clone().to(sd[k].dtype)
+    module.load_state_dict(sd, strict=True)
+    return module.to(DEV)
+
+
+@pytest.mark.parametrize("variant", ["std", "fast"])
+@pytest.mark.parametrize("mode", ["spatial", "temporal"])
+def test_operator_module_vs_reference_golden(variant, mode):
+    z = load_npz(f"op_{variant}_{mode}.npz")
+    shp = z["x"].shape
+    n, cin, t, v = (shp if variant == "std" else (shp[0], shp[3], shp[1], shp[2]))
+    cout = z["p.conv_f.weight"].shape[0]
+    ref_c, kpt = (t, v) if mode == "spatial" else (v, t)
+    op = _load(_mod(variant).DSTDGC(cin, cout, ref_c, kpt, mode=mode), split(z, "p."))
+    x, A, alpha = (z[k].float().to(DEV).requires_grad_(True) for k in ("x", "A", "alpha"))
+    y = op(x, A, alpha)
+    assert y.is_contiguous() and max_abs(y, z["y"]) < 1e-4
+    (y * z["gy"].float().to(DEV)).sum().backward()
+    assert rel_err(x.grad, z["g_x"]) < 1e-4
+    assert rel_err(A.grad, z["g_A"]) < 1e-4
+    assert rel_err(alpha.grad, z["g_alpha"]) < 1e-4
+    for k, gref in split(z, "g.").items():
+        got = dict(op.named_parameters())[k].grad
+        assert max_abs(got, gref) < 1e-4 * max(1.0, float(gref.abs().max())), k
+
+
+@pytest.mark.parametrize("variant", ["std", "fast"])
+@pytest.mark.parametrize("tag,cin,cout", [("in", 6, 8), ("mid", 8, 8), ("out", 8, 3)])
+def test_block_module_vs_reference_golden(variant, tag, cin, cout):
+    z = load_npz(f"block_{variant}_{tag}.npz")
+    blk = _load(_mod(variant).DSTDGCB(cin, cout, 12, 22, "h36m"), split(z, "p.")).train()
+    x = z["x"].float().to(DEV).requires_grad_(True)
+    y = blk(x)
+    assert max_abs(y, z["y"]) < 1e-4 * max(1.0, float(z["y"].abs().max()) / 10)
+    (y * z["gy"].float().to(DEV)).sum().backward()
+    assert rel_err(x.grad, z["g_x"]) < 1e-4
+    named = dict(blk.named_parameters())
+    for k, gref in split(z, "g.").items():
+        # parameters feeding straight into a BN have an exactly-zero true gradient: absolute tolerance
+        assert max_abs(named[k].grad, gref) < 2e-4 * max(1.0, float(gref.abs().max())), k
+    sd = blk.state_dict()
+    for k, b in split(z, "after.").items():
+        assert max_abs(sd[k], b) < 1e-5 * max(1.0, float(b.abs().max())), k
+    blk.eval()
+    with torch.no_grad():
+        ye = blk(z["x"].float().to(DEV))
+    assert max_abs(ye, z["y_eval"]) < 1e-4 * max(1.0, float(z["y_eval"].abs().max()))
+
+
+@pytest.mark.parametrize("name,v,layout", [("std_h36m", 22, "h36m"), ("std_cmu", 25, "cmu"), ("std_3dpw", 23, "3dpw"),
+                                           ("fast_h36m", 22, "h36m")])
+def test_model_vs_reference_golden(name, v, layout):
+    z = load_npz(f"model_{name}.npz")
+    variant = name.split("_")[0]
+    m = _load(_mod(variant).DSTDGCN(6, 4, 6, 0.0, v, 8, 2, layout), split(z, "p.")).train()
+    x = z["x"].float().to(DEV).requires_grad_(True)
+    y = m(x)
+    assert max_abs(y, z["y"]) < 2e-4 * max(1.0, float(z["y"].abs().max()))
+    loss = y.pow(2).mean()
+    loss.backward()
+    assert rel_err(x.grad, z["g_x"]) < 1e-3
+    named = dict(m.named_parameters())
+    for k, gref in split(z, "g.").items():
+        assert max_abs(named[k].grad, gref) < 1e-3 * max(1.0, float(gref.abs().max())), k
+    m.eval()
+    with torch.no_grad():
+        assert rel_err(m(z["x"].float().to(DEV)), z["y_eval"]) < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["std", "fast"])
+def test_training_steps_vs_reference_golden(variant):
+    """Three steps of the reference engine loop (ModelWrapper + mpjpe + Adam, inverse=True) vs our TrainStep."""
+    from dstd_gcn_b200.engine import TrainStep
+    z = load_npz(f"train_{variant}.npz")
+    m = _load(_mod(variant).DSTDGCN(6, 4, 6, 0.0, 22, 8, 2, "h36m"), split(z, "p.")).train()
+    step = TrainStep(m, lr=3e-3, inverse=True)
+    losses = []
+    for s in range(3):
+        losses.append(float(step(z[f"inputs{s}"].float().to(DEV), z[f"inputs_inv{s}"].float().to(DEV),
+                                 z[f"targets{s}"].float().to(DEV))))
+    ref = z["losses"].double()
+    assert float((torch.tensor(losses, dtype=torch.float64) - ref).abs().max() / ref.abs().max()) < 1e-3
+    sd = m.state_dict()
+    for k, b in split(z, "after.").items():
+        if b.is_floating_point():
+            assert max_abs(sd[k], b) < 2e-3 * max(1.0, float(b.abs().max())), k
+        else:
+            assert int(sd[k]) == int(b), k
+
+
+# ================================================================================================= full-size checks
+def _perturbed(m):
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            leaf = k.split(".")[-1]
+            if leaf in ("alpha_sm", "alpha_tm"):
+                p.fill_(0.1)
+            elif leaf == "W_s":
+                p.fill_(0.05)
+            elif leaf == "R_t":
+                p.fill_(0.01)
+    return m
+
+
+@pytest.mark.parametrize("variant,layout,v,tin,tout", [("std", "h36m", 22, 10, 25), ("std", "cmu", 25, 10, 25),
+                                                        ("std", "3dpw", 23, 10, 30), ("fast", "h36m", 22, 10, 25)])
+def test_full_size_model_vs_oracle(variant, layout, v, tin, tout):
+    """BASELINE.json shapes (C=64, L=5): fp32 kernels vs the fp64 oracle; the bar is relative because the reference's
+    own fp32-vs-fp64 error at this depth is 2e-3 abs / 4e-5 rel on y and 3e-3 rel on dx."""
+    from oracle import dstd_oracle as orc
+    torch.manual_seed(777)
+    m = _perturbed(_mod(variant).DSTDGCN(6, tin, tout, 0.0, v, 64, 5, layout))
+    p64 = orc.state_from_module(m, torch.float64)
+    x = torch.randn(4, tin + tout, v, 3, generator=torch.Generator().manual_seed(1234), dtype=torch.float64)
+    x64 = x.clone().requires_grad_(True)
+    y64 = orc.dstdgcn(x64, p64, True, variant == "fast")
+    y64.pow(2).mean().backward()
+    m = m.to(DEV).train()
+    xd = x.float().to(DEV).requires_grad_(True)
+    y = m(xd)
+    y.pow(2).mean().backward()
+    assert rel_err(y, y64) < 2e-4
+    assert rel_err(xd.grad, x64.grad) < 1e-2
+    worst = 0.0
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            g64 = p64[k].grad
+            worst = max(worst, float((p.grad.double().cpu() - g64).abs().max() / (g64.abs().max() + 1e-3)))
+    assert worst < 2e-2, worst
+
+
+def test_eval_is_batch_independent_at_full_batch():
+    """Size-independent property at BASELINE batch size: in eval mode each sample is processed independently, so the
+    result of sample i does not depend on the batch it travels in (checks every per-sample tiling/indexing path)."""
+    torch.manual_seed(3)
+    m = _perturbed(_mod("std").DSTDGCN(6, 10, 25, 0.0, 22, 64, 5, "h36m")).to(DEV).train()
+    x = torch.randn(256, 35, 22, 3, device=DEV)
+    with torch.no_grad():
+        m(x)                      # one training-mode pass to move the running statistics off (0, 1)
+        m.eval()
+        y_all = m(x)
+        y_part = m(x[100:117])
+        y_one = m(x[255:256])
+    assert max_abs(y_all[100:117], y_part) < 1e-5 * float(y_all.abs().max())
+    assert max_abs(y_all[255:256], y_one) < 1e-5 * float(y_all.abs().max())
+
+
+def test_no_cpu_fallback():
+    from dstd_gcn_b200.model import dstdgcn as std
+    m = std.DSTDGCN(6, 4, 6, 0.0, 22, 8, 1, "h36m")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 10, 22, 3))
