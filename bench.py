@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--workload", default="h36m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -239,8 +240,15 @@ def main():
     host = [synthetic_batch(args.batch, t, v, t_in, seed=777 + rank * 1000 + i) for i in range(nbuf)]
     host = [tuple(x.pin_memory() for x in b) for b in host]
     resident = [tuple(x.to(dev) for x in b) for b in host]
-    stage = [tuple(torch.empty_like(x, device=dev) for x in host[0]) for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    launches_per_step = None
+    if not args.no_graph:
+        l0 = be.launches
+        step.capture(*resident[0])            # whole step -> one CUDA graph (state rolled back after its warm-up)
+        launches_per_step = (be.launches - l0) // 3       # 2 warm-up steps + the captured one
+        stage = [step._static]
+    else:
+        stage = [tuple(torch.empty_like(x, device=dev) for x in host[0]) for _ in range(2)]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -254,7 +262,7 @@ def main():
 
     def run_e2e(k):
         for i in range(k):
-            hb, db = host[i % nbuf], stage[i % 2]
+            hb, db = host[i % nbuf], stage[i % len(stage)]
             for h, d in zip(hb, db):
                 d.copy_(h, non_blocking=True)
             loss = step(*db)
@@ -272,7 +280,7 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), be.launches - l0
+        return float(ms), (launches_per_step * k if launches_per_step is not None else be.launches - l0)
 
     run_resident(args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -303,7 +311,7 @@ def main():
             "model_passes_per_s": 2.0 * sps,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "cuda_graph": not args.no_graph,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,

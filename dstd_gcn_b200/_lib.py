@@ -105,7 +105,8 @@ SYMBOLS = {
     "dstd_mpjpe_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dstd_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float,
-                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "dstd_last_error": (C.c_char_p, []),
     "dstd_version": (C.c_char_p, []),
     "dstd_kernel_launch_count": (C.c_int, []),
@@ -375,10 +376,16 @@ class CudaBackend:
                                                       _ptr(ws), ws.numel(), _stream()), "dstd_mpjpe_forward_backward")
         return gpred
 
-    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step):
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
+                  lr_dev=None, step_dev=None):
+        if lr_dev is not None:
+            _check(lr_dev, "lr_dev")
+        if step_dev is not None:
+            _check(step_dev, "step_dev", torch.int32)
         self._ok(self.lib.dstd_adam_step(_cptr(param, "param"), _cptr(grad, "grad"), _cptr(exp_avg, "exp_avg"),
                                          _cptr(exp_avg_sq, "exp_avg_sq"), param.numel(), lr, beta1, beta2, eps,
-                                         weight_decay, grad_scale, int(step), _stream()), "dstd_adam_step")
+                                         weight_decay, grad_scale, int(step), _ptr(lr_dev), _ptr(step_dev),
+                                         _stream()), "dstd_adam_step")
 
 
 _backend = None

@@ -138,7 +138,7 @@ static int agg_fwd_launch(const AggParams& q, cudaStream_t st) {
   DSTD_REQUIRE(smem <= 220 * 1024, DSTD_ERR_UNSUPPORTED, "aggregate_fwd: Cin=%d K=%d needs %zu B shared memory", q.Cin,
                q.K, smem);
   auto kern = aggregate_fwd_kernel<KMAX>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024) ensure_max_smem((const void*)kern);
   dim3 grid(cdiv(q.P, PCH), q.N);
   kern<<<grid, 32 * PCH, smem, st>>>(q, PCH, RS);
   count_launch();
@@ -313,7 +313,7 @@ static int agg_bwd_launch(const AggParams& q, cudaStream_t st) {
   DSTD_REQUIRE(smem <= 220 * 1024, DSTD_ERR_UNSUPPORTED, "aggregate_bwd: Cin=%d K=%d needs %zu B shared memory", q.Cin,
                q.K, smem);
   auto kern = aggregate_bwd_kernel<KMAX>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024) ensure_max_smem((const void*)kern);
   dim3 grid(cdiv(q.P, PCH), q.N);
   kern<<<grid, 32 * PCH, smem, st>>>(q, PCH);
   count_launch();

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
+#include <set>
 
 #include "kernels.cuh"
 
@@ -25,6 +27,15 @@ int check_launch(const char* what) {
     return DSTD_ERR_CUDA;
   }
   return DSTD_OK;
+}
+
+void ensure_max_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(kernel)) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  done.insert(kernel);
 }
 
 struct GcWs {

@@ -12,6 +12,8 @@ namespace dstd {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> status (+message)
+void ensure_max_smem(const void* kernel);  // one-time opt-in to 227 KB dynamic shared memory (capture-safe afterwards)
+constexpr int MAX_DYN_SMEM = 227 * 1024;
 
 #define DSTD_REQUIRE(cond, code, ...)      \
   do {                                     \

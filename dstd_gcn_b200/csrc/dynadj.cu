@@ -98,7 +98,7 @@ static int dynadj_fwd_launch(const DynAdjFwdParams& q, cudaStream_t st) {
   if (smem > 48 * 1024) {
     DSTD_REQUIRE(smem <= 220 * 1024, DSTD_ERR_UNSUPPORTED, "dynadj_fwd: P=%d K=%d needs %zu B shared memory", q.P, q.K,
                  smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_max_smem((const void*)kern);
   }
   kern<<<dim3(q.N, q.nb), threads, smem, st>>>(q);
   count_launch();
@@ -328,7 +328,7 @@ int launch_dynadj_bwd(const DynAdjBwdParams& q, cudaStream_t st) {
 #define DSTD_DYN_BWD(A, C)                                                                        \
   {                                                                                               \
     auto kern = dynadj_bwd_kernel<A, C>;                                                          \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (smem > 48 * 1024) ensure_max_smem((const void*)kern);                                                  \
     kern<<<grid, 256, smem, st>>>(q, g.RV, g.ECP, g.WLD);                                         \
   }
   if (tma <= 3 && tna <= 2) DSTD_DYN_BWD(3, 2)

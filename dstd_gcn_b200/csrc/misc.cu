@@ -146,7 +146,14 @@ __global__ void mpjpe_finish_kernel(const float* __restrict__ partial, int nblk,
 // ------------------------------------------------------------------------------------------ Adam
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                            float gs, float bc1, float bc2_sqrt) {
+                            float gs, float bc1, float bc2_sqrt, const float* __restrict__ lr_dev,
+                            const int* __restrict__ step_dev) {
+  if (lr_dev) lr = __ldg(lr_dev);
+  if (step_dev) {
+    const float s = (float)__ldg(step_dev);
+    bc1 = -expm1f(s * log1pf(b1 - 1.f));          // 1 - b1^s without cancellation
+    bc2_sqrt = sqrtf(-expm1f(s * log1pf(b2 - 1.f)));
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * gs;
     float pi = p[i];
@@ -226,13 +233,15 @@ extern "C" int dstd_mpjpe_forward_backward(const float* pred, const float* targe
 
 extern "C" int dstd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
-                              dstd_stream_t stream) {
-  DSTD_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step > 0, DSTD_ERR_BAD_ARG, "adam_step: bad args");
+                              const float* lr_dev, const int* step_dev, dstd_stream_t stream) {
+  DSTD_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && (step > 0 || step_dev), DSTD_ERR_BAD_ARG,
+               "adam_step: bad args");
+  if (step <= 0) step = 1;
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                   eps, weight_decay, grad_scale, (float)bc1,
-                                                                  (float)sqrt(bc2));
+                                                                  (float)sqrt(bc2), lr_dev, step_dev);
   count_launch();
   return check_launch("adam");
 }

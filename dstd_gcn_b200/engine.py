@@ -72,6 +72,18 @@ class TrainStep:
         self.step_count = 0
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        dev = self.flat.param.device
+        # learning rate and step count also live on the device so that a captured CUDA graph of the step stays valid
+        # across steps and StepLR updates (engine/prediction.py:193-196,310)
+        self.lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.graph = None
+        self._static = None
+        self._static_loss = None
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
 
     def grad_of(self, name):
         off, n, shape = self.flat.slices[name]
@@ -91,7 +103,7 @@ class TrainStep:
         loss.backward()
         return loss.detach()
 
-    def __call__(self, inputs, inputs_inv, targets):
+    def _eager(self, inputs, inputs_inv, targets):
         loss = self.loss_and_grads(inputs, inputs_inv, targets)
         if self.world > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
@@ -99,11 +111,58 @@ class TrainStep:
         if self.clip > 0:
             gn = torch.linalg.vector_norm(self.flat.grad) * gscale
             self.flat.grad.mul_(torch.clamp(self.clip / (gn + 1e-6), max=1.0))
-        self.step_count += 1
+        self.step_dev.add_(1)
         torch.ops.dstd_b200.adam_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr,
-                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, gscale,
-                                      self.step_count)
+                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, gscale, 0,
+                                      self.lr_dev, self.step_dev)
         return loss
+
+    def __call__(self, inputs, inputs_inv, targets):
+        self.step_count += 1
+        if self.graph is not None and tuple(inputs.shape) == tuple(self._static[0].shape):
+            for dst, src in zip(self._static, (inputs, inputs_inv, targets)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self.graph.replay()
+            return self._static_loss
+        return self._eager(inputs, inputs_inv, targets)
+
+    # ------------------------------------------------------------------ CUDA graph of the whole step
+    def _snapshot(self):
+        bufs = {k: b.clone() for k, b in self.model.named_buffers()}
+        return (self.flat.param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone(), bufs,
+                torch.cuda.get_rng_state(self.flat.param.device))
+
+    def _restore(self, snap):
+        prm, m, v, st, bufs, rng = snap
+        self.flat.param.copy_(prm)
+        self.exp_avg.copy_(m)
+        self.exp_avg_sq.copy_(v)
+        self.step_dev.copy_(st)
+        for k, b in self.model.named_buffers():
+            b.copy_(bufs[k])
+        torch.cuda.set_rng_state(rng, self.flat.param.device)
+
+    def capture(self, inputs, inputs_inv, targets, warmup=2):
+        """Capture one whole step (both forwards, backward, all-reduce, Adam: several hundred launches) into a CUDA
+        graph bound to static input buffers.  The warm-up steps needed before capture are rolled back, so capturing
+        does not change the training state.  Later calls with the same batch shape replay the graph."""
+        self._static = tuple(t.clone() for t in (inputs, inputs_inv, targets))
+        snap = self._snapshot()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        self._restore(snap)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._static_loss = self._eager(*self._static)
+        self._restore(snap)       # capture itself does not execute, but keep the invariant explicit
+        self.graph = g
+        return self
 
 
 @torch.no_grad()

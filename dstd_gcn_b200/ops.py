@@ -184,8 +184,10 @@ def _(pred, target, loss, scale, accumulate):
 
 @torch.library.custom_op("dstd_b200::adam_step", mutates_args=("param", "exp_avg", "exp_avg_sq"))
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float, beta2: float,
-              eps: float, weight_decay: float, grad_scale: float, step: int) -> None:
-    _lib.backend().adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step)
+              eps: float, weight_decay: float, grad_scale: float, step: int, lr_dev: Optional[Tensor] = None,
+              step_dev: Optional[Tensor] = None) -> None:
+    _lib.backend().adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
+                             lr_dev, step_dev)
 
 
 # =========================================================================== autograd

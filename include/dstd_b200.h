@@ -212,14 +212,16 @@ int dstd_finish_backward(const float* gy, dstd_view gz, float* gx, int N, int T,
  *           gpred = scale * d loss / d pred.
  *   adam  : torch.optim.Adam semantics (no amsgrad, no weight decay unless wd != 0, coupled L2) on a
  *           flat parameter bucket; `step` is the 1-based step count; grad is multiplied by grad_scale
- *           first (1/world_size after an all-reduce(sum)).
+ *           first (1/world_size after an all-reduce(sum)).  When `lr_dev` / `step_dev` are non-NULL the kernel reads
+ *           the learning rate / step count from device memory instead (so that a CUDA graph of the whole training
+ *           step stays valid across steps and StepLR updates).
  * ------------------------------------------------------------------------------------------- */
 size_t dstd_mpjpe_workspace_bytes(long long J);
 int dstd_mpjpe_forward_backward(const float* pred, const float* target, long long J, float scale, int accumulate,
                                 float* loss_out, float* gpred, void* ws, size_t ws_bytes, dstd_stream_t stream);
 int dstd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
-                   dstd_stream_t stream);
+                   const float* lr_dev, const int* step_dev, dstd_stream_t stream);
 
 /* misc */
 const char* dstd_last_error(void);

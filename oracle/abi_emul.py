@@ -247,7 +247,12 @@ class EmulBackend:
         g = torch.where(nrm[:, None] > 0, d / nrm.clamp_min(1e-30)[:, None], torch.zeros_like(d)) * (scale / j)
         return g.reshape(pred.shape)
 
-    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step):
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
+                  lr_dev=None, step_dev=None):
+        if lr_dev is not None:
+            lr = float(lr_dev)
+        if step_dev is not None:
+            step = int(step_dev)
         g = grad * grad_scale
         if weight_decay != 0:
             g = g + weight_decay * param
