@@ -87,6 +87,7 @@ class ChmixBwdArgs(C.Structure):
 
 # every symbol include/dstd_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
+    "dstd_gc_needs_xa": (C.c_int, [C.c_int] * 5),
     "dstd_gc_fwd_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "dstd_gc_bwd_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "dstd_gc_forward": (C.c_int, [C.POINTER(GcFwdArgs), C.c_void_p]),
@@ -221,7 +222,9 @@ class CudaBackend:
         out = _like_layout(xu, cout)
         m = torch.empty((n, nb, 4, p_, k_), dtype=torch.float32, device=dev)
         pd = torch.empty((n, nb, p_, k_, k_), dtype=torch.float32, device=dev)
-        xa = torch.empty((n, nb, cin + 1, p_, k_), dtype=torch.float32, device=dev)
+        # the aggregated tile is only kept for shapes whose backward cannot recompute it on chip
+        need_xa = bool(self.lib.dstd_gc_needs_xa(cin, cout, p_, k_, nb))
+        xa = torch.empty((n, nb, cin + 1, p_, k_) if need_xa else (0,), dtype=torch.float32, device=dev)
         ws = self._ws(self.lib.dstd_gc_fwd_workspace_bytes(n, cin, cout, p_, k_, nb), dev)
         a = GcFwdArgs()
         a.N, a.Cin, a.Cout, a.P, a.K, a.nb = n, cin, cout, p_, k_, nb
@@ -229,7 +232,7 @@ class CudaBackend:
         a.x, a.out, a.skip = _view(xu, "x"), _view(out, "out"), _view(skip_u, "skip")
         a.alpha = _cptr(alpha, "alpha")
         self._fill_branches(a.br, brs)
-        a.m, a.pd, a.xa = _ptr(m), _ptr(pd), _ptr(xa)
+        a.m, a.pd, a.xa = _ptr(m), _ptr(pd), (_ptr(xa) if xa.numel() else None)
         a.ws, a.ws_bytes = _ptr(ws), ws.numel()
         self._ok(self.lib.dstd_gc_forward(C.byref(a), _stream()), "dstd_gc_forward")
         return out, m, pd, xa
@@ -248,7 +251,7 @@ class CudaBackend:
         a.x, a.gout, a.gx = _view(xu, "x"), _view(gout_u, "gout"), _view(gx, "gx")
         a.alpha = _cptr(alpha, "alpha")
         self._fill_branches(a.br, brs)
-        a.m, a.pd, a.xa = _cptr(m, "m"), _cptr(pd, "pd"), _cptr(xa, "xa")
+        a.m, a.pd, a.xa = _cptr(m, "m"), _cptr(pd, "pd"), (_cptr(xa, "xa") if xa is not None and xa.numel() else None)
         grads = []
         for i, br in enumerate(brs):
             g = {k: torch.empty_like(br[k]) for k in _GR_KEYS}

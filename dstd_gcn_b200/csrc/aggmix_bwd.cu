@@ -1,0 +1,430 @@
+// Fused backward of (adjacency aggregation + channel mix) of one DSTD-GC unit: everything between the unit's output
+// gradient and the gradient of the dynamic adjacency (Appendix A of SURVEY.md; reference autograd of
+// model/dstdgcn.py:81,87,93 for all branches of DSTDGCB.forward :145-150 / :157-161).
+//
+// Persistent CTAs walk the work items (sample n, chunk of PCH frames).  Per item and branch b, with the frame chunk
+// of x, gout and the adjacency xm_b = alpha*pd + A_eff staged in shared memory (frames padded to KP = 4*ceil(K/4) so
+// that every row / frame is float4 aligned):
+//   (a) gxa_b[j][pos]   = sum_o wcat[o][b,j] gout[o][pos]                    j <= Cin (row Cin: the conv_f bias)
+//   (b) xa_b [j][pos]   = sum_v x[j][l,v] xmu_b[l][v][w]   (recomputed, never stored in HBM)
+//   (c) gWf_b[o][j]    += sum_pos gout[o][pos] xa_b[j][pos]                  register accumulators for the whole CTA life
+//   (d) gx[c][l,v]     += sum_w gxa_b[c][l,w] xmu_b[l][v][w]
+//   (e) gxmu_b[l][v][w] = sum_{c<=Cin} xaug[c][l,v] gxa_b[c][l,w]  -> gxm in HBM (consumed by the dynadj backward)
+// HBM traffic per sample: x, gout read once, gx written once, pd read / gxm written once (K/ C of a tile each).
+// The per-CTA weight-gradient partials are summed by reduce_segments (deterministic, fixed order).
+#include "kernels.cuh"
+
+namespace dstd {
+
+template <int KP, int TN>
+__global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int WH = (KP / 2 + 3) / 4 * 4;   // half of a padded adjacency row, multiple of 4
+  constexpr int KP2 = 2 * WH;
+  const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, C1 = Cin + 1, Cout = q.Cout, nb = q.nb, PCH = q.PCH;
+  const int LD = q.LD, CinP = q.CinP;
+  const int npos_pad = PCH * KP;
+  float* xs = smem;                         // [C1][LD]    (row Cin = ones on valid positions)
+  float* gos = xs + C1 * LD;                // [Cout][LD]
+  float* gxas = gos + Cout * LD;            // [C1][LD]
+  float* xas = gxas + C1 * LD;              // [C1][LD]
+  float* gxs = xas + C1 * LD;               // [Cin][LD]
+  float* xms = gxs + Cin * LD;              // [nb][PCH][K][KP2]   xmu[l][v][w]
+  float* xmT = xms + nb * PCH * K * KP2;    // [nb][PCH][K][KP2]   xmu[l][w][v]
+  float* wfB = xmT + nb * PCH * K * KP2;    // [nb][Cout][CinP]
+  float* bfs = wfB + nb * Cout * CinP;      // [nb][Cout]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
+  const int nchunk = (P + PCH - 1) / PCH;
+  const long long nitems = (long long)q.N * nchunk;
+
+  // ---- once per CTA: weights
+  for (int i = tid; i < nb * Cout * CinP; i += 256) {
+    int c = i % CinP, t = i / CinP;
+    int o = t % Cout, b = t / Cout;
+    wfB[i] = c < Cin ? __ldg(q.w_f[b] + (long long)o * Cin + c) : 0.f;
+  }
+  for (int i = tid; i < nb * Cout; i += 256) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
+
+  // persistent weight-gradient accumulators: warp = 8 output channels, lane = input channels (lane, lane+32)
+  float accw[DSTD_MAX_BRANCH][8][2];
+  float accb[DSTD_MAX_BRANCH];
+#pragma unroll
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+    accb[b] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) accw[b][r][0] = accw[b][r][1] = 0.f;
+  }
+  const int o0 = warp * 8;
+
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int n = (int)(item / nchunk), p0 = (int)(item - (long long)n * nchunk) * PCH;
+    const int pv = min(PCH, P - p0);
+    __syncthreads();   // previous item fully consumed (also orders the one-time weight staging)
+
+    // ---- stage x (+ ones row), gout, adjacency (both orientations)
+    {
+      const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
+      for (int i = tid; i < C1 * npos_pad; i += 256) {
+        int c = i / npos_pad, j = i - c * npos_pad;
+        int l = j / KP, k = j - l * KP;
+        float v = 0.f;
+        if (l < pv && k < K)
+          v = c < Cin ? __ldg(xb + (long long)c * q.x.sc + (long long)l * q.x.sp + (long long)k * q.x.sk) : 1.0f;
+        xs[c * LD + j] = v;
+      }
+      const float* gb = q.gout.p + (long long)n * q.gout.sn + (long long)p0 * q.gout.sp;
+      for (int i = tid; i < Cout * npos_pad; i += 256) {
+        int c = i / npos_pad, j = i - c * npos_pad;
+        int l = j / KP, k = j - l * KP;
+        float v = 0.f;
+        if (l < pv && k < K) v = __ldg(gb + (long long)c * q.gout.sc + (long long)l * q.gout.sp + (long long)k * q.gout.sk);
+        gos[c * LD + j] = v;
+      }
+      for (int i = tid; i < nb * PCH * K * KP2; i += 256) {
+        int w = i % KP2, t = i / KP2;
+        int v = t % K;
+        t /= K;
+        int l = t % PCH, b = t / PCH;
+        float val = 0.f, valT = 0.f;
+        if (w < K && l < pv) {
+          // xmu[v][w] = xm[v][w] (or xm[w][v] when adj_t);  row (v) of xms, row (v as "w") of xmT
+          const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0 + l) * KK;
+          int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
+          int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
+          float a = __ldg(q.adj[b] + e), aT = __ldg(q.adj[b] + eT);
+          if (q.adj_w[b]) { a *= __ldg(q.adj_w[b] + e); aT *= __ldg(q.adj_w[b] + eT); }
+          if (q.adj_r[b]) { a += __ldg(q.adj_r[b] + e); aT += __ldg(q.adj_r[b] + eT); }
+          val = fmaf(alpha, __ldg(pdl + e), a);
+          valT = fmaf(alpha, __ldg(pdl + eT), aT);
+        }
+        xms[i] = val;
+        xmT[i] = valT;
+      }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {   // unrolled: accw[b] must stay in registers
+      if (b >= nb) break;
+      // ================= (a) gxa_b = wcat_b^T gout    (warp = 8 rows j, lane = positions)
+      for (int j0 = warp * 8; j0 < Cin; j0 += 64) {
+        float acc[8][TN];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int i = 0; i < TN; ++i) acc[r][i] = 0.f;
+        const float* wrow = wfB + (b * Cout) * CinP + j0;
+#pragma unroll 2
+        for (int o = 0; o < Cout; ++o) {
+          const float4 wa = *reinterpret_cast<const float4*>(wrow + o * CinP);
+          const float4 wb = *reinterpret_cast<const float4*>(wrow + o * CinP + 4);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+          float gv[TN];
+#pragma unroll
+          for (int i = 0; i < TN; ++i) gv[i] = gos[o * LD + lane + 32 * i];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < TN; ++i) acc[r][i] = fmaf(wv[r], gv[i], acc[r][i]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (j0 + r < Cin) {
+#pragma unroll
+            for (int i = 0; i < TN; ++i)
+              if (lane + 32 * i < npos_pad) gxas[(j0 + r) * LD + lane + 32 * i] = acc[r][i];
+          }
+        }
+      }
+      // bias row: gxa[Cin][pos] = sum_o bf[o] gout[o][pos]
+      for (int pos = tid; pos < npos_pad; pos += 256) {
+        float s = 0.f;
+        for (int o = 0; o < Cout; ++o) s = fmaf(bfs[b * Cout + o], gos[o * LD + pos], s);
+        gxas[Cin * LD + pos] = s;
+      }
+
+      // ================= (b) xa_b recompute    (warp = (frame, w half), lane = channel pair)
+      for (int it = warp; it < 2 * pv; it += 8) {
+        const int l = it >> 1, half = it & 1;
+        const float* xm_l = xms + ((b * PCH + l) * K) * KP2 + half * WH;
+        for (int cg = 0; cg < Cin; cg += 64) {
+          const int c0 = cg + lane, c1 = c0 + 32;
+          const bool v0ok = c0 < Cin, v1ok = c1 < Cin;
+          float x0[KP], x1[KP];
+#pragma unroll
+          for (int i = 0; i < KP / 4; ++i) {
+            const float4 t0 = *reinterpret_cast<const float4*>(xs + (v0ok ? c0 : 0) * LD + l * KP + 4 * i);
+            const float4 t1 = *reinterpret_cast<const float4*>(xs + (v1ok ? c1 : 0) * LD + l * KP + 4 * i);
+            x0[4 * i] = t0.x; x0[4 * i + 1] = t0.y; x0[4 * i + 2] = t0.z; x0[4 * i + 3] = t0.w;
+            x1[4 * i] = t1.x; x1[4 * i + 1] = t1.y; x1[4 * i + 2] = t1.z; x1[4 * i + 3] = t1.w;
+          }
+          float a0[WH], a1[WH];
+#pragma unroll
+          for (int j = 0; j < WH; ++j) a0[j] = a1[j] = 0.f;
+#pragma unroll
+          for (int v = 0; v < KP; ++v) {
+            if (v < K) {
+              const float4* r4 = reinterpret_cast<const float4*>(xm_l + v * KP2);
+#pragma unroll
+              for (int j4 = 0; j4 < WH / 4; ++j4) {
+                const float4 m = r4[j4];
+                a0[j4 * 4 + 0] = fmaf(x0[v], m.x, a0[j4 * 4 + 0]);
+                a0[j4 * 4 + 1] = fmaf(x0[v], m.y, a0[j4 * 4 + 1]);
+                a0[j4 * 4 + 2] = fmaf(x0[v], m.z, a0[j4 * 4 + 2]);
+                a0[j4 * 4 + 3] = fmaf(x0[v], m.w, a0[j4 * 4 + 3]);
+                a1[j4 * 4 + 0] = fmaf(x1[v], m.x, a1[j4 * 4 + 0]);
+                a1[j4 * 4 + 1] = fmaf(x1[v], m.y, a1[j4 * 4 + 1]);
+                a1[j4 * 4 + 2] = fmaf(x1[v], m.z, a1[j4 * 4 + 2]);
+                a1[j4 * 4 + 3] = fmaf(x1[v], m.w, a1[j4 * 4 + 3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < WH / 4; ++j4) {
+            if (half * WH + 4 * j4 < KP) {
+              if (v0ok)
+                *reinterpret_cast<float4*>(xas + c0 * LD + l * KP + half * WH + 4 * j4) =
+                    make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
+              if (v1ok)
+                *reinterpret_cast<float4*>(xas + c1 * LD + l * KP + half * WH + 4 * j4) =
+                    make_float4(a1[4 * j4], a1[4 * j4 + 1], a1[4 * j4 + 2], a1[4 * j4 + 3]);
+            }
+          }
+        }
+        if (lane < WH && half * WH + lane < KP) {   // ones row: column sums of xmu (zero on padded columns)
+          float s = 0.f;
+          for (int v = 0; v < K; ++v) s += xm_l[v * KP2 + lane];
+          xas[Cin * LD + l * KP + half * WH + lane] = s;
+        }
+      }
+      // frames beyond pv: xa must read as zero in (c)
+      for (int i = tid; i < C1 * (PCH - pv) * KP; i += 256) {
+        int c = i / ((PCH - pv) * KP), j = i - c * ((PCH - pv) * KP);
+        xas[c * LD + pv * KP + j] = 0.f;
+      }
+      __syncthreads();
+
+      // ================= (c) weight gradient: accw[b][r][i] += sum_pos gout[o0+r][pos] xa_b[lane+32i][pos]
+      if (o0 < Cout) {
+        const int j0c = min(lane, Cin - 1), j1c = min(lane + 32, Cin - 1);
+        const int nr = min(8, Cout - o0);
+        for (int p4 = 0; p4 < npos_pad; p4 += 4) {
+          const float4 b0 = *reinterpret_cast<const float4*>(xas + j0c * LD + p4);
+          const float4 b1 = *reinterpret_cast<const float4*>(xas + j1c * LD + p4);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < nr) {
+              const float4 a = *reinterpret_cast<const float4*>(gos + (o0 + r) * LD + p4);
+              accw[b][r][0] = fmaf(a.x, b0.x, accw[b][r][0]);
+              accw[b][r][0] = fmaf(a.y, b0.y, accw[b][r][0]);
+              accw[b][r][0] = fmaf(a.z, b0.z, accw[b][r][0]);
+              accw[b][r][0] = fmaf(a.w, b0.w, accw[b][r][0]);
+              accw[b][r][1] = fmaf(a.x, b1.x, accw[b][r][1]);
+              accw[b][r][1] = fmaf(a.y, b1.y, accw[b][r][1]);
+              accw[b][r][1] = fmaf(a.z, b1.z, accw[b][r][1]);
+              accw[b][r][1] = fmaf(a.w, b1.w, accw[b][r][1]);
+            }
+          }
+        }
+      }
+      if (tid < Cout) {   // bias gradient: sum_pos gout[o][pos] * (column sums of xmu)
+        float s = 0.f;
+        for (int p4 = 0; p4 < npos_pad; p4 += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(gos + tid * LD + p4);
+          const float4 c = *reinterpret_cast<const float4*>(xas + Cin * LD + p4);
+          s = fmaf(a.x, c.x, s); s = fmaf(a.y, c.y, s); s = fmaf(a.z, c.z, s); s = fmaf(a.w, c.w, s);
+        }
+        accb[b] += s;
+      }
+
+      // ================= (d) gx += gxa_b xmu_b^T    (warp = (frame, v half), lane = channel pair)
+      for (int it = warp; it < 2 * pv; it += 8) {
+        const int l = it >> 1, half = it & 1;
+        const float* xmT_l = xmT + ((b * PCH + l) * K) * KP2 + half * WH;
+        for (int cg = 0; cg < Cin; cg += 64) {
+          const int c0 = cg + lane, c1 = c0 + 32;
+          const bool v0ok = c0 < Cin, v1ok = c1 < Cin;
+          float g0[KP], g1[KP];
+#pragma unroll
+          for (int i = 0; i < KP / 4; ++i) {
+            const float4 t0 = *reinterpret_cast<const float4*>(gxas + (v0ok ? c0 : 0) * LD + l * KP + 4 * i);
+            const float4 t1 = *reinterpret_cast<const float4*>(gxas + (v1ok ? c1 : 0) * LD + l * KP + 4 * i);
+            g0[4 * i] = t0.x; g0[4 * i + 1] = t0.y; g0[4 * i + 2] = t0.z; g0[4 * i + 3] = t0.w;
+            g1[4 * i] = t1.x; g1[4 * i + 1] = t1.y; g1[4 * i + 2] = t1.z; g1[4 * i + 3] = t1.w;
+          }
+          float a0[WH], a1[WH];
+#pragma unroll
+          for (int j = 0; j < WH; ++j) a0[j] = a1[j] = 0.f;
+#pragma unroll
+          for (int w = 0; w < KP; ++w) {
+            if (w < K) {
+              const float4* r4 = reinterpret_cast<const float4*>(xmT_l + w * KP2);
+#pragma unroll
+              for (int j4 = 0; j4 < WH / 4; ++j4) {
+                const float4 m = r4[j4];
+                a0[j4 * 4 + 0] = fmaf(g0[w], m.x, a0[j4 * 4 + 0]);
+                a0[j4 * 4 + 1] = fmaf(g0[w], m.y, a0[j4 * 4 + 1]);
+                a0[j4 * 4 + 2] = fmaf(g0[w], m.z, a0[j4 * 4 + 2]);
+                a0[j4 * 4 + 3] = fmaf(g0[w], m.w, a0[j4 * 4 + 3]);
+                a1[j4 * 4 + 0] = fmaf(g1[w], m.x, a1[j4 * 4 + 0]);
+                a1[j4 * 4 + 1] = fmaf(g1[w], m.y, a1[j4 * 4 + 1]);
+                a1[j4 * 4 + 2] = fmaf(g1[w], m.z, a1[j4 * 4 + 2]);
+                a1[j4 * 4 + 3] = fmaf(g1[w], m.w, a1[j4 * 4 + 3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < WH / 4; ++j4) {
+            if (half * WH + 4 * j4 < KP) {
+              if (v0ok) {
+                float4* d = reinterpret_cast<float4*>(gxs + c0 * LD + l * KP + half * WH + 4 * j4);
+                float4 t = make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
+                if (b > 0) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+                *d = t;
+              }
+              if (v1ok) {
+                float4* d = reinterpret_cast<float4*>(gxs + c1 * LD + l * KP + half * WH + 4 * j4);
+                float4 t = make_float4(a1[4 * j4], a1[4 * j4 + 1], a1[4 * j4 + 2], a1[4 * j4 + 3]);
+                if (b > 0) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+                *d = t;
+              }
+            }
+          }
+        }
+      }
+
+      // ================= (e) gxmu_b[l][v][w] = sum_{c<=Cin} xaug[c][l,v] gxa_b[c][l,w]   (4x4 tiles) -> HBM
+      {
+        constexpr int NT4 = KP / 4;
+        const int ntile = pv * NT4 * NT4;
+        for (int tile = tid; tile < ntile; tile += 256) {
+          const int wt = tile % NT4;
+          int t = tile / NT4;
+          const int vt = t % NT4, l = t / NT4;
+          float acc[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+          const float* xp = xs + l * KP + 4 * vt;
+          const float* gp = gxas + l * KP + 4 * wt;
+#pragma unroll 4
+          for (int c = 0; c < C1; ++c) {
+            const float4 xv = *reinterpret_cast<const float4*>(xp + c * LD);
+            const float4 gv = *reinterpret_cast<const float4*>(gp + c * LD);
+            const float xa_[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float ga_[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa_[i], ga_[j], acc[i][j]);
+          }
+          float* dst = q.gxm + ((long long)(n * nb + b) * P + p0 + l) * KK;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int v = 4 * vt + i;
+            if (v >= K) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int w = 4 * wt + j;
+              if (w < K) dst[q.adj_t ? (w * K + v) : (v * K + w)] = acc[i][j];
+            }
+          }
+        }
+      }
+      __syncthreads();   // gxas / xas are rewritten by the next branch
+    }
+
+    // ---- gx chunk -> HBM (coalesced along the contiguous (l,k) run of each channel)
+    {
+      const int npos = pv * K;
+      float* gb = q.gx.p + (long long)n * q.gx.sn + (long long)p0 * q.gx.sp;
+      for (int i = tid; i < Cin * npos; i += 256) {
+        int c = i / npos, j = i - c * npos;
+        int l = j / K, k = j - l * K;
+        gb[(long long)c * q.gx.sc + (long long)l * q.gx.sp + (long long)k * q.gx.sk] = gxs[c * LD + l * KP + k];
+      }
+    }
+  }
+
+  // ---- per-CTA partials of the conv_f gradients
+  float* pw = q.part_w + (long long)blockIdx.x * nb * Cout * Cin;
+  float* pb = q.part_b + (long long)blockIdx.x * nb * Cout;
+#pragma unroll
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+    if (b < nb) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int o = o0 + r;
+        if (o < Cout) {
+          if (lane < Cin) pw[((long long)b * Cout + o) * Cin + lane] = accw[b][r][0];
+          if (lane + 32 < Cin) pw[((long long)b * Cout + o) * Cin + lane + 32] = accw[b][r][1];
+        }
+      }
+      if (tid < Cout) pb[b * Cout + tid] = accb[b];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ launch
+struct AggMixBwdGeom {
+  int KP, TN, PCH, LD, CinP;
+  size_t smem;
+};
+
+static bool aggmix_bwd_geom(int Cin, int Cout, int P, int K, int nb, AggMixBwdGeom& g) {
+  if (K > 40 || K < 1 || Cin > 64 || Cout > 64) return false;
+  g.KP = K <= 24 ? 24 : K <= 28 ? 28 : K <= 36 ? 36 : 40;
+  const int WH = (g.KP / 2 + 3) / 4 * 4, KP2 = 2 * WH, C1 = Cin + 1;
+  g.CinP = (Cin + 7) / 8 * 8;
+  for (int pch = 128 / g.KP; pch >= 1; --pch) {
+    if (pch > P && pch > 1) continue;
+    const int npad = pch * g.KP;
+    int ld = npad + 4;
+    if ((ld / 4) % 2 == 0) ld += 4;
+    size_t f = (size_t)(3 * C1 + Cout + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * Cout * g.CinP +
+               (size_t)nb * Cout + 16;
+    if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 512) {
+      g.PCH = pch;
+      g.LD = ld;
+      g.TN = npad <= 96 ? 3 : 4;
+      g.smem = f * sizeof(float);
+      return true;
+    }
+  }
+  return false;
+}
+
+bool aggmix_bwd_supported(int Cin, int Cout, int P, int K, int nb) {
+  AggMixBwdGeom g;
+  return aggmix_bwd_geom(Cin, Cout, P, K, nb, g);
+}
+
+int aggmix_bwd_ctas(int N, int P, int K, int Cin, int Cout, int nb) {
+  AggMixBwdGeom g;
+  if (!aggmix_bwd_geom(Cin, Cout, P, K, nb, g)) return 0;
+  long long items = (long long)N * ((P + g.PCH - 1) / g.PCH);
+  return (int)(items < 148 ? items : 148);
+}
+
+int launch_aggmix_bwd(AggMixBwdParams q, cudaStream_t st) {
+  AggMixBwdGeom g;
+  DSTD_REQUIRE(aggmix_bwd_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g), DSTD_ERR_UNSUPPORTED,
+               "aggmix_bwd: Cin=%d Cout=%d K=%d outside the compiled tile limits", q.Cin, q.Cout, q.K);
+  q.PCH = g.PCH; q.LD = g.LD; q.CinP = g.CinP;
+  const int ctas = aggmix_bwd_ctas(q.N, q.P, q.K, q.Cin, q.Cout, q.nb);
+#define DSTD_AMB(KP_, TN_)                                           \
+  if (g.KP == KP_ && g.TN == TN_) {                                  \
+    auto kern = aggmix_bwd_kernel<KP_, TN_>;                         \
+    ensure_max_smem((const void*)kern);                              \
+    kern<<<ctas, 256, g.smem, st>>>(q);                              \
+  }
+  DSTD_AMB(24, 3) DSTD_AMB(24, 4) DSTD_AMB(28, 3) DSTD_AMB(28, 4)
+  DSTD_AMB(36, 3) DSTD_AMB(36, 4) DSTD_AMB(40, 3) DSTD_AMB(40, 4)
+#undef DSTD_AMB
+  count_launch();
+  return check_launch("aggmix_bwd");
+}
+
+}  // namespace dstd

@@ -46,14 +46,17 @@ struct GcWs {
 };
 
 static size_t gc_fwd_ws(int Cin, int Cout, int nb) {
-  return arena_need({(size_t)Cout * nb * (Cin + 1) * 4, (size_t)4 * nb * (Cin + 1) * 4});
+  return arena_need({(size_t)Cout * nb * (Cin + 1) * 4, (size_t)4 * nb * (Cin + 1) * 4,
+                     (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4});
 }
 static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   const size_t C1 = Cin + 1, G = (size_t)N * P * K;
   const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N);
-  return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, G * nb * C1 * 4, G * nb * K * 4,
-                     G * nb * 4 * 4, (size_t)S1 * Cout * nb * C1 * 4, (size_t)S1 * 4 * nb * C1 * 4,
-                     (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4});
+  const size_t unf = aggmix_bwd_supported(Cin, Cout, P, K, nb) ? 0 : 1;   // buffers only the unfused path needs
+  return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
+                     G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, (size_t)S1 * 4 * nb * C1 * 4,
+                     (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4,
+                     (size_t)148 * nb * Cout * Cin * 4, (size_t)148 * nb * Cout * 4});
 }
 
 static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const dstd_branch* br, const char* fn) {
@@ -68,7 +71,9 @@ static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const
   return DSTD_OK;
 }
 
-static void fill_pack(PackParams& pk, int Cin, int Cout, int nb, const dstd_branch* br, float* wcat, float* wm) {
+static void fill_pack(PackParams& pk, int Cin, int Cout, int nb, const dstd_branch* br, float* wcat, float* wm,
+                      float* wcatT = nullptr) {
+  pk.wcatT = wcatT;
   pk.Cin = Cin; pk.Cout = Cout; pk.nb = nb;
   for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
     const dstd_branch& s = br[b < nb ? b : 0];
@@ -102,6 +107,9 @@ extern "C" const char* dstd_last_error(void) { return g_err; }
 extern "C" const char* dstd_version(void) { return "dstd_b200 0.1 sm_100a"; }
 extern "C" int dstd_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+extern "C" int dstd_gc_needs_xa(int Cin, int Cout, int P, int K, int nb) {
+  return (aggmix_supported(Cin, Cout, P, K, nb) && aggmix_bwd_supported(Cin, Cout, P, K, nb)) ? 0 : 1;
+}
 extern "C" size_t dstd_gc_fwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb) {
   (void)N; (void)P; (void)K;
   return gc_fwd_ws(Cin, Cout, nb);
@@ -115,7 +123,7 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   DSTD_REQUIRE(a, DSTD_ERR_BAD_ARG, "gc_forward: null args");
   int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_forward");
   if (rc) return rc;
-  DSTD_REQUIRE(a->x.ptr && a->out.ptr && a->m && a->pd && a->xa, DSTD_ERR_BAD_ARG, "gc_forward: null tensor");
+  DSTD_REQUIRE(a->x.ptr && a->out.ptr && a->m && a->pd, DSTD_ERR_BAD_ARG, "gc_forward: null tensor");
   DSTD_REQUIRE(a->ws && a->ws_bytes >= gc_fwd_ws(a->Cin, a->Cout, a->nb), DSTD_ERR_WORKSPACE,
                "gc_forward: workspace too small (%zu < %zu)", a->ws_bytes, gc_fwd_ws(a->Cin, a->Cout, a->nb));
   cudaStream_t st = (cudaStream_t)stream;
@@ -124,9 +132,11 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   Arena ar(a->ws, a->ws_bytes);
   float* wcat = ar.take<float>((size_t)Cout * nb * C1);
   float* wm = ar.take<float>((size_t)4 * nb * C1);
+  float* wcatT = ar.take<float>((size_t)nb * C1 * ((Cout + 7) / 8 * 8));
+  const bool fused = aggmix_supported(Cin, Cout, P, K, nb);
 
   PackParams pk;
-  fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm);
+  fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm, fused ? wcatT : nullptr);
   if ((rc = launch_pack(pk, st))) return rc;
 
   // 1. m = [conv_m1; conv_m2] x + b        (all branches in one pass over x)
@@ -146,6 +156,24 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
     dp.b_rm[b] = a->br[b < nb ? b : 0].b_rm;
   }
   if ((rc = launch_dynadj_fwd(dp, st))) return rc;
+
+  // 3+4 fused: out = wcat ([x;1] (alpha pd + A)) (+ skip); the aggregated tile stays in shared memory
+  if (fused) {
+    AggMixParams am;
+    am.N = N; am.Cin = Cin; am.Cout = Cout; am.P = P; am.K = K; am.nb = nb;
+    am.adj_t = (a->flags & DSTD_FLAG_ADJ_T) ? 1 : 0;
+    am.PCH = 0; am.CoutP = 0;
+    am.x = mk(a->x); am.out = mk(a->out); am.skip = mk(a->skip);
+    am.pd = a->pd; am.alpha = a->alpha;
+    for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+      const dstd_branch& s = a->br[b < nb ? b : 0];
+      am.adj[b] = s.adj; am.adj_w[b] = s.adj_w; am.adj_r[b] = s.adj_r;
+    }
+    am.wcatT = wcatT;
+    am.xa = a->xa;
+    return launch_aggmix_fwd(am, st);
+  }
+  DSTD_REQUIRE(a->xa, DSTD_ERR_BAD_ARG, "gc_forward: the unfused path needs the xa buffer");
 
   // 3. xa = [x;1] (alpha pd + A)           (aggregation before the channel mix)
   AggParams ag;
@@ -168,8 +196,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   DSTD_REQUIRE(a, DSTD_ERR_BAD_ARG, "gc_backward: null args");
   int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_backward");
   if (rc) return rc;
-  DSTD_REQUIRE(a->x.ptr && a->gout.ptr && a->gx.ptr && a->m && a->pd && a->xa, DSTD_ERR_BAD_ARG,
-               "gc_backward: null tensor");
+  DSTD_REQUIRE(a->x.ptr && a->gout.ptr && a->gx.ptr && a->m && a->pd, DSTD_ERR_BAD_ARG, "gc_backward: null tensor");
   const int N = a->N, Cin = a->Cin, Cout = a->Cout, P = a->P, K = a->K, nb = a->nb, C1 = Cin + 1;
   const size_t need = gc_bwd_ws(N, Cin, Cout, P, K, nb);
   DSTD_REQUIRE(a->ws && a->ws_bytes >= need, DSTD_ERR_WORKSPACE, "gc_backward: workspace too small (%zu < %zu)",
@@ -180,18 +207,41 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   Arena ar(a->ws, a->ws_bytes);
   float* wcat = ar.take<float>((size_t)Cout * nb * C1);
   float* wm = ar.take<float>((size_t)4 * nb * C1);
-  float* gxa = ar.take<float>((size_t)G * nb * C1);
+  const bool fused = aggmix_bwd_supported(Cin, Cout, P, K, nb);
+  float* gxa = ar.take<float>(fused ? 0 : (size_t)G * nb * C1);
   float* gxm = ar.take<float>((size_t)G * nb * K);
   float* gm = ar.take<float>((size_t)G * nb * 4);
-  float* p_wcat = ar.take<float>((size_t)S1 * Cout * nb * C1);
+  float* p_wcat = ar.take<float>(fused ? 0 : (size_t)S1 * Cout * nb * C1);
   float* p_wm = ar.take<float>((size_t)S1 * 4 * nb * C1);
   float* p_wrm = ar.take<float>((size_t)S2 * nb * P * (2 * P + 1));
   float* p_adj = ar.take<float>((size_t)S2 * nb * K * K);
   float* p_alpha = ar.take<float>((size_t)S2 * nb);
+  float* p_wf = ar.take<float>((size_t)148 * nb * Cout * Cin);
+  float* p_bf = ar.take<float>((size_t)148 * nb * Cout);
 
   PackParams pk;
   fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm);
   if ((rc = launch_pack(pk, st))) return rc;
+
+  int S1a = 0, n_wf = 0;
+  if (fused) {
+    // 1-3 fused: gxa, xa (recomputed), g(wcat), gx (aggregation part), gxm without leaving the SM
+    AggMixBwdParams am;
+    am.N = N; am.Cin = Cin; am.Cout = Cout; am.P = P; am.K = K; am.nb = nb;
+    am.adj_t = (a->flags & DSTD_FLAG_ADJ_T) ? 1 : 0;
+    am.PCH = am.LD = am.CinP = 0;
+    am.x = mk(a->x); am.gout = mk(a->gout); am.gx = mk(a->gx);
+    am.pd = a->pd; am.alpha = a->alpha;
+    for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+      const dstd_branch& s = a->br[b < nb ? b : 0];
+      am.adj[b] = s.adj; am.adj_w[b] = s.adj_w; am.adj_r[b] = s.adj_r;
+      am.w_f[b] = s.w_f; am.b_f[b] = s.b_f;
+    }
+    am.gxm = gxm; am.part_w = p_wf; am.part_b = p_bf;
+    if ((rc = launch_aggmix_bwd(am, st))) return rc;
+    n_wf = aggmix_bwd_ctas(N, P, K, Cin, Cout, nb);
+  } else {
+  DSTD_REQUIRE(a->xa, DSTD_ERR_BAD_ARG, "gc_backward: the unfused path needs the saved xa buffer");
 
   // 1. gxa = wcat^T gout
   BgemmParams g1;
@@ -210,7 +260,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   w1.b_ones_row = -1;
   w1.partial = p_wcat;
   if ((rc = launch_wgrad(w1, st))) return rc;
-  const int S1a = w1.S;
+  S1a = w1.S;
 
   // 3. aggregation backward: gx (first contribution), gxm
   AggParams ag;
@@ -219,6 +269,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   ag.gx = mk(a->gx);
   ag.gxm = gxm;
   if ((rc = launch_aggregate_bwd(ag, st))) return rc;
+  }
 
   // 4. dynamic adjacency backward: gm, partial gWrm/gbrm, gA_eff, galpha
   DynAdjBwdParams db;
@@ -245,6 +296,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   w2.b_ones_row = Cin;
   w2.partial = p_wm;
   if ((rc = launch_wgrad(w2, st))) return rc;
+  const int S1b = w2.S;
 
   // 7. reduce the split partials and scatter them into the parameter gradients
   ReduceParams rp;
@@ -260,12 +312,17 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   const int P21 = 2 * P + 1;
   for (int b = 0; b < nb; ++b) {
     const dstd_branch_grad& g = a->gbr[b];
-    seg(p_wcat + b * C1, S1a, st_wcat, Cout, Cin, nb * C1, g.w_f, Cin);
-    seg(p_wcat + b * C1 + Cin, S1a, st_wcat, Cout, 1, nb * C1, g.b_f, 1);
-    seg(p_wm + (b * 4 + 0) * C1, S1a, st_wm, 2, Cin, C1, g.w_m1, Cin);
-    seg(p_wm + (b * 4 + 0) * C1 + Cin, S1a, st_wm, 2, 1, C1, g.b_m1, 1);
-    seg(p_wm + (b * 4 + 2) * C1, S1a, st_wm, 2, Cin, C1, g.w_m2, Cin);
-    seg(p_wm + (b * 4 + 2) * C1 + Cin, S1a, st_wm, 2, 1, C1, g.b_m2, 1);
+    if (fused) {
+      seg(p_wf + (long long)b * Cout * Cin, n_wf, (long long)nb * Cout * Cin, Cout, Cin, Cin, g.w_f, Cin);
+      seg(p_bf + (long long)b * Cout, n_wf, (long long)nb * Cout, Cout, 1, 1, g.b_f, 1);
+    } else {
+      seg(p_wcat + b * C1, S1a, st_wcat, Cout, Cin, nb * C1, g.w_f, Cin);
+      seg(p_wcat + b * C1 + Cin, S1a, st_wcat, Cout, 1, nb * C1, g.b_f, 1);
+    }
+    seg(p_wm + (b * 4 + 0) * C1, S1b, st_wm, 2, Cin, C1, g.w_m1, Cin);
+    seg(p_wm + (b * 4 + 0) * C1 + Cin, S1b, st_wm, 2, 1, C1, g.b_m1, 1);
+    seg(p_wm + (b * 4 + 2) * C1, S1b, st_wm, 2, Cin, C1, g.w_m2, Cin);
+    seg(p_wm + (b * 4 + 2) * C1 + Cin, S1b, st_wm, 2, 1, C1, g.b_m2, 1);
     seg(p_wrm + (long long)b * P * P21, S2, (long long)nb * P * P21, P, 2 * P, P21, g.w_rm, 2 * P);
     seg(p_wrm + (long long)b * P * P21 + 2 * P, S2, (long long)nb * P * P21, P, 1, P21, g.b_rm, 1);
     float* gadjw = a->br[b].adj_w ? g.adj_w : nullptr;

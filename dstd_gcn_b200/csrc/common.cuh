@@ -68,8 +68,12 @@ __device__ __forceinline__ long long vix(const View4& v, int n, int c, int p, in
 // tanh with ~3e-7 absolute error: 1 - 2/(exp(2x)+1) through ex2.approx / rcp (two MUFU ops).
 // (tanh.approx.f32 is ~5e-4 relative: too coarse for the 1e-4 parity budget once scaled by conv_rm.)
 __device__ __forceinline__ float fast_tanh(float x) {
+#ifdef DSTD_ACCURATE_TANH
+  return tanhf(x);
+#else
   float e = exp2f(x * 2.885390081777927f);  // exp(2x); ex2.approx, saturates to inf / 0
   return 1.0f - __fdividef(2.0f, e + 1.0f);
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

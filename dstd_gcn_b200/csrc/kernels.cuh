@@ -99,6 +99,46 @@ int launch_aggregate_fwd(const AggParams& q, cudaStream_t st);
 int launch_aggregate_bwd(const AggParams& q, cudaStream_t st);
 bool aggregate_supported(int Cin, int P, int K);
 
+// ------------------------------------------------------------------ aggmix.cu
+struct AggMixParams {
+  int N, Cin, Cout, P, K, nb, adj_t;
+  int PCH, CoutP;      // filled by the launcher
+  View4 x;             // [N,Cin,P,K]
+  View4 out;           // [N,Cout,P,K]
+  View4 skip;          // optional
+  const float* pd;     // [N,nb,P,K,K]
+  const float* alpha;
+  const float* adj[DSTD_MAX_BRANCH];
+  const float* adj_w[DSTD_MAX_BRANCH];
+  const float* adj_r[DSTD_MAX_BRANCH];
+  const float* wcatT;  // [nb*(Cin+1)][CoutP] from the pack kernel
+  float* xa;           // optional [N,nb,Cin+1,P,K]
+};
+int launch_aggmix_fwd(AggMixParams q, cudaStream_t st);
+bool aggmix_supported(int Cin, int Cout, int P, int K, int nb);
+
+// ------------------------------------------------------------------ aggmix_bwd.cu
+struct AggMixBwdParams {
+  int N, Cin, Cout, P, K, nb, adj_t;
+  int PCH, LD, CinP;   // filled by the launcher
+  View4 x;             // [N,Cin,P,K]
+  View4 gout;          // [N,Cout,P,K]
+  View4 gx;            // [N,Cin,P,K] written (aggregation part of the input gradient)
+  const float* pd;     // [N,nb,P,K,K]
+  const float* alpha;
+  const float* adj[DSTD_MAX_BRANCH];
+  const float* adj_w[DSTD_MAX_BRANCH];
+  const float* adj_r[DSTD_MAX_BRANCH];
+  const float* w_f[DSTD_MAX_BRANCH];   // [Cout][Cin]
+  const float* b_f[DSTD_MAX_BRANCH];   // [Cout]
+  float* gxm;          // [N,nb,P,K,K] written
+  float* part_w;       // [ctas][nb][Cout][Cin]
+  float* part_b;       // [ctas][nb][Cout]
+};
+int launch_aggmix_bwd(AggMixBwdParams q, cudaStream_t st);
+bool aggmix_bwd_supported(int Cin, int Cout, int P, int K, int nb);
+int aggmix_bwd_ctas(int N, int P, int K, int Cin, int Cout, int nb);
+
 // ------------------------------------------------------------------ bn_act.cu
 int bn_act_splits(int N);
 
@@ -113,6 +153,7 @@ struct PackParams {
   const float* b_m2[DSTD_MAX_BRANCH];
   float* wcat;         // [Cout][nb*(Cin+1)]
   float* wm;           // [4*nb][Cin+1]
+  float* wcatT;        // optional [nb*(Cin+1)][CoutP], CoutP = Cout rounded up to 8, zero padded
 };
 int launch_pack(const PackParams& q, cudaStream_t st);
 

@@ -11,8 +11,17 @@ namespace dstd {
 __global__ void pack_kernel(PackParams q) {
   const int C1 = q.Cin + 1, ld = q.nb * C1;
   const int n1 = q.Cout * ld, n2 = 4 * q.nb * C1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
-    if (i < n1) {
+  const int CoutP = (q.Cout + 7) / 8 * 8;
+  const int n3 = q.wcatT ? ld * CoutP : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
+    if (i >= n1 + n2) {
+      int k = i - n1 - n2;
+      int j = k / CoutP, o = k - j * CoutP;
+      int b = j / C1, c = j - b * C1;
+      float v = 0.f;
+      if (o < q.Cout) v = c < q.Cin ? __ldg(q.w_f[b] + (long long)o * q.Cin + c) : __ldg(q.b_f[b] + o);
+      q.wcatT[k] = v;
+    } else if (i < n1) {
       int o = i / ld, rem = i - o * ld;
       int b = rem / C1, c = rem - b * C1;
       q.wcat[i] = c < q.Cin ? __ldg(q.w_f[b] + (long long)o * q.Cin + c) : __ldg(q.b_f[b] + o);
@@ -30,6 +39,7 @@ __global__ void pack_kernel(PackParams q) {
 
 int launch_pack(const PackParams& q, cudaStream_t st) {
   int total = q.Cout * q.nb * (q.Cin + 1) + 4 * q.nb * (q.Cin + 1);
+  if (q.wcatT) total += q.nb * (q.Cin + 1) * ((q.Cout + 7) / 8 * 8);
   pack_kernel<<<min(cdiv(total, 256), 64), 256, 0, st>>>(q);
   count_launch();
   return check_launch("pack");

@@ -51,8 +51,9 @@ def gc_fwd(x: Tensor, alpha: Optional[Tensor], br: Sequence[Optional[Tensor]], s
 def _(x, alpha, br, skip, nb, adj_t):
     n, cin, p, k = x.shape
     cout = br[6].shape[0]
+    need_xa = bool(_lib.load_library().dstd_gc_needs_xa(cin, cout, p, k, nb))
     return (_lib._like_layout(x, cout), x.new_empty((n, nb, 4, p, k)), x.new_empty((n, nb, p, k, k)),
-            x.new_empty((n, nb, cin + 1, p, k)))
+            x.new_empty((n, nb, cin + 1, p, k) if need_xa else (0,)))
 
 
 @torch.library.custom_op("dstd_b200::gc_bwd", mutates_args=())

@@ -80,7 +80,7 @@ typedef struct {
  *   xa[n,b,c,p,w]   = sum_v x[n,c,p,v] xm[n,b,p,v,w]   (row c = Cin: x := 1, i.e. column sums of xm)
  *   out[n,o,p,w]    = sum_b ( sum_c Wf_b[o,c] xa[n,b,c,p,w] + bf_b[o] xa[n,b,Cin,p,w] ) (+ skip)
  * With DSTD_FLAG_ADJ_T the aggregation uses xm[n,b,p,w,v] instead (fast variant).
- * m, pd, xa are written and must be kept for the backward call.
+ * m, pd (and xa, see dstd_gc_needs_xa) are written and must be kept for the backward call.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int N, Cin, Cout, P, K, nb, flags;
@@ -91,7 +91,7 @@ typedef struct {
   dstd_branch br[DSTD_MAX_BRANCH];
   float* m;              /* [N,nb,4,P,K] */
   float* pd;             /* [N,nb,P,K,K] */
-  float* xa;             /* [N,nb,Cin+1,P,K] */
+  float* xa;             /* [N,nb,Cin+1,P,K]; NULL allowed when !dstd_gc_needs_xa() */
   void* ws;              /* workspace, dstd_gc_fwd_workspace_bytes() */
   size_t ws_bytes;
 } dstd_gc_fwd_args;
@@ -112,6 +112,9 @@ typedef struct {
   size_t ws_bytes;
 } dstd_gc_bwd_args;
 
+/* 1 when dstd_gc_backward for this shape reads the saved `xa` (unfused fallback); 0 when the fused backward recomputes
+ * it on chip, in which case `xa` may be NULL in both calls. */
+int dstd_gc_needs_xa(int Cin, int Cout, int P, int K, int nb);
 size_t dstd_gc_fwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb);
 size_t dstd_gc_bwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb);
 int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream);

@@ -23,8 +23,10 @@ def run(dtype, m, x):
 
 def main():
     torch.manual_seed(777)
-    m = perturb(std.DSTDGCN(6, 10, 25, 0.0, 22, 64, 5, "h36m"))
-    x = torch.randn(4, 35, 22, 3, generator=torch.Generator().manual_seed(1234), dtype=torch.float64)
+    layout = sys.argv[1] if len(sys.argv) > 1 else "h36m"
+    v, tin, tout = {"h36m": (22, 10, 25), "cmu": (25, 10, 25), "3dpw": (23, 10, 30)}[layout]
+    m = perturb(std.DSTDGCN(6, tin, tout, 0.0, v, 64, 5, layout))
+    x = torch.randn(4, tin + tout, v, 3, generator=torch.Generator().manual_seed(1234), dtype=torch.float64)
     y64, gx64, g64 = run(torch.float64, m, x)
     y32, gx32, g32 = run(torch.float32, m, x)
     md = m.to("cuda").train()
