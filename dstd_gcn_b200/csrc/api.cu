@@ -54,7 +54,7 @@ static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N);
   const size_t unf = aggmix_bwd_supported(Cin, Cout, P, K, nb) ? 0 : 1;   // buffers only the unfused path needs
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
-                     G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, (size_t)S1 * 4 * nb * C1 * 4,
+                     G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, (size_t)(S1 > 296 ? S1 : 296) * 4 * nb * C1 * 4,
                      (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4,
                      (size_t)148 * nb * Cout * Cin * 4, (size_t)148 * nb * Cout * 4});
 }
@@ -212,7 +212,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   float* gxm = ar.take<float>((size_t)G * nb * K);
   float* gm = ar.take<float>((size_t)G * nb * 4);
   float* p_wcat = ar.take<float>(fused ? 0 : (size_t)S1 * Cout * nb * C1);
-  float* p_wm = ar.take<float>((size_t)S1 * 4 * nb * C1);
+  float* p_wm = ar.take<float>((size_t)(S1 > 296 ? S1 : 296) * 4 * nb * C1);
   float* p_wrm = ar.take<float>((size_t)S2 * nb * P * (2 * P + 1));
   float* p_adj = ar.take<float>((size_t)S2 * nb * K * K);
   float* p_alpha = ar.take<float>((size_t)S2 * nb);
@@ -279,24 +279,31 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   db.S = S2; db.part_wrm = p_wrm; db.part_adj = p_adj; db.part_alpha = p_alpha;
   if ((rc = launch_dynadj_bwd(db, st))) return rc;
 
-  // 5. gx += wm^T gm
-  BgemmParams g2;
-  g2.M = Cin; g2.Kd = 4 * nb; g2.G = G; g2.P = P; g2.K = K;
-  g2.w = wm; g2.wsc = C1; g2.wsi = 1; g2.bias = nullptr;
-  g2.in = dense_view(gm, 4 * nb, P, K); g2.ones_row = -1;
-  g2.out = mk(a->gx);
-  g2.add = mk(a->gx);
-  if ((rc = launch_bgemm(g2, st))) return rc;
-
-  // 6. g(wm)[j, c] = sum gm[j] [x;1][c]
-  WgradParams w2;
-  w2.M = 4 * nb; w2.Cd = C1; w2.G = G; w2.P = P; w2.K = K;
-  w2.a = dense_view(gm, 4 * nb, P, K);
-  w2.b = mk(a->x);
-  w2.b_ones_row = Cin;
-  w2.partial = p_wm;
-  if ((rc = launch_wgrad(w2, st))) return rc;
-  const int S1b = w2.S;
+  // 5+6. gx += wm^T gm ; g(wm)[j, c] = sum gm[j] [x;1][c]   (one pass over x)
+  int S1b = 0;
+  if (mproj_bwd_supported(Cin, 4 * nb)) {
+    MprojBwdParams mp;
+    mp.Cin = Cin; mp.J = 4 * nb; mp.P = P; mp.K = K; mp.G = G;
+    mp.x = mk(a->x); mp.gx = mk(a->gx); mp.gm = gm; mp.wm = wm; mp.partial = p_wm;
+    if ((rc = launch_mproj_bwd(mp, st))) return rc;
+    S1b = mproj_bwd_ctas(G);
+  } else {
+    BgemmParams g2;
+    g2.M = Cin; g2.Kd = 4 * nb; g2.G = G; g2.P = P; g2.K = K;
+    g2.w = wm; g2.wsc = C1; g2.wsi = 1; g2.bias = nullptr;
+    g2.in = dense_view(gm, 4 * nb, P, K); g2.ones_row = -1;
+    g2.out = mk(a->gx);
+    g2.add = mk(a->gx);
+    if ((rc = launch_bgemm(g2, st))) return rc;
+    WgradParams w2;
+    w2.M = 4 * nb; w2.Cd = C1; w2.G = G; w2.P = P; w2.K = K;
+    w2.a = dense_view(gm, 4 * nb, P, K);
+    w2.b = mk(a->x);
+    w2.b_ones_row = Cin;
+    w2.partial = p_wm;
+    if ((rc = launch_wgrad(w2, st))) return rc;
+    S1b = w2.S;
+  }
 
   // 7. reduce the split partials and scatter them into the parameter gradients
   ReduceParams rp;

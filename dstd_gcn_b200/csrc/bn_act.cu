@@ -13,12 +13,13 @@
 
 namespace dstd {
 
-constexpr int BN_MAXJ = 4;       // positions per thread  -> T*V <= 4096
-constexpr int BN_THREADS_MAX = 1024;
+constexpr int BN_THREADS_MAX = 512;
+constexpr int BN_MAXJ = 8;       // positions per thread  -> T*V <= 4096
+constexpr int BN_U = 4;          // samples in flight per thread (memory-level parallelism)
 
 int bn_act_splits(int N) {
-  int s = N < 16 ? N : 16 + (N - 16) / 8;   // ~8 samples per CTA for large batches
-  if (s > 64) s = 64;
+  int s = (N + 7) / 8;            // ~8 samples per CTA
+  if (s > 128) s = 128;
   if (s < 1) s = 1;
   return s;
 }
@@ -29,26 +30,28 @@ struct BnGeom {
 static BnGeom bn_geom(int T, int V) {
   int tv = T * V;
   BnGeom g;
-  g.nj = cdiv(tv, BN_THREADS_MAX);
+  int nj = cdiv(tv, BN_THREADS_MAX);
+  g.nj = nj <= 1 ? 1 : nj <= 2 ? 2 : nj <= 4 ? 4 : 8;
   g.threads = cdiv(cdiv(tv, g.nj), 32) * 32;
   return g;
 }
 
 // position j (0..TV) in the memory order of view `v` -> logical (t, v)
+__device__ __forceinline__ bool t_fastest(const View4& vw) { return !(vw.sk == 1 || vw.sp != 1); }
 __device__ __forceinline__ void decode_pos(const View4& vw, int j, int T, int V, int& t, int& v) {
-  if (vw.sk == 1 || vw.sp != 1) {   // V fastest (or generic): j = t*V + v
+  if (!t_fastest(vw)) {   // V fastest (or generic): j = t*V + v
     t = j / V;
     v = j - t * V;
-  } else {                          // T fastest: j = v*T + t
+  } else {                // T fastest: j = v*T + t
     v = j / T;
     t = j - v * T;
   }
 }
-__device__ __forceinline__ bool same_order(const View4& a, const View4& b) {
-  bool at = !(a.sk == 1 || a.sp != 1), bt = !(b.sk == 1 || b.sp != 1);
-  return at == bt;
-}
+__device__ __forceinline__ bool same_order(const View4& a, const View4& b) { return t_fastest(a) == t_fastest(b); }
 __device__ __forceinline__ int bn_pidx(int c, int v, int C, int V, int vc_order) { return vc_order ? v * C + c : c * V + v; }
+__device__ __forceinline__ long long pos_off(const View4& vw, int t, int v) {
+  return (long long)t * vw.sp + (long long)v * vw.sk;
+}
 
 struct BnFwdP {
   int N, C, T, V, vc_order, training, S;
@@ -63,45 +66,72 @@ struct BnFwdP {
   float* part;   // [S][C][V][2]
 };
 
+// stage BN_U planes of `src` (walked in its own memory order, coalesced) into sh[u][t*V+v]
+template <int NJ>
+__device__ __forceinline__ void stage_planes(const View4& src, int c, int n, int n1, int T, int V, float* sh, int TV) {
+  float tmp[BN_U][NJ];
+  int idx[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const int j = threadIdx.x + i * blockDim.x;
+    idx[i] = -1;
+    if (j < TV) {
+      int t, v;
+      decode_pos(src, j, T, V, t, v);
+      idx[i] = t * V + v;
+      const float* p = src.p + (long long)n * src.sn + (long long)c * src.sc + pos_off(src, t, v);
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) tmp[u][i] = (n + u < n1) ? __ldg(p + (long long)u * src.sn) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i)
+    if (idx[i] >= 0) {
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) sh[u * TV + idx[i]] = tmp[u][i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ forward: statistics
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_stats_kernel(BnFwdP q, int nj) {
+template <int NJ>
+__global__ void __launch_bounds__(BN_THREADS_MAX) bn_stats_kernel(BnFwdP q) {
   extern __shared__ float sh[];   // [2][T*V]
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
-  float a1[BN_MAXJ], a2[BN_MAXJ];
+  float a1[NJ], a2[NJ];
+  int idx[NJ];
 #pragma unroll
-  for (int i = 0; i < BN_MAXJ; ++i) {
+  for (int i = 0; i < NJ; ++i) {
     a1[i] = a2[i] = 0.f;
-    if (i < nj) {
-      int j = threadIdx.x + i * blockDim.x;
-      if (j < TV) {
-        int t, v;
-        decode_pos(q.y, j, T, V, t, v);
-        const float shift = __ldg(q.y.p + vix(q.y, 0, c, 0, v));
-        const float* p = q.y.p + vix(q.y, n0, c, t, v);
-        float s1 = 0.f, s2 = 0.f;
-        for (int n = n0; n < n1; ++n, p += q.y.sn) {
-          float d = __ldg(p) - shift;
-          s1 += d;
-          s2 = fmaf(d, d, s2);
+    idx[i] = -1;
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < TV) {
+      int t, v;
+      decode_pos(q.y, j, T, V, t, v);
+      idx[i] = t * V + v;
+      const float shift = __ldg(q.y.p + vix(q.y, 0, c, 0, v));
+      const float* p = q.y.p + (long long)c * q.y.sc + pos_off(q.y, t, v);
+      float s1 = 0.f, s2 = 0.f;
+      for (int n = n0; n < n1; n += BN_U) {
+        float d[BN_U];
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) d[u] = (n + u < n1) ? __ldg(p + (long long)(n + u) * q.y.sn) - shift : 0.f;
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          s1 += d[u];
+          s2 = fmaf(d[u], d[u], s2);
         }
-        a1[i] = s1;
-        a2[i] = s2;
       }
+      a1[i] = s1;
+      a2[i] = s2;
     }
   }
 #pragma unroll
-  for (int i = 0; i < BN_MAXJ; ++i) {
-    if (i < nj) {
-      int j = threadIdx.x + i * blockDim.x;
-      if (j < TV) {
-        int t, v;
-        decode_pos(q.y, j, T, V, t, v);
-        sh[t * V + v] = a1[i];
-        sh[TV + t * V + v] = a2[i];
-      }
+  for (int i = 0; i < NJ; ++i)
+    if (idx[i] >= 0) {
+      sh[idx[i]] = a1[i];
+      sh[TV + idx[i]] = a2[i];
     }
-  }
   __syncthreads();
   if (threadIdx.x < V) {
     int v = threadIdx.x;
@@ -151,65 +181,61 @@ __global__ void bn_eval_stats_kernel(BnFwdP q) {
 }
 
 // ------------------------------------------------------------------------------------------ forward: apply
-// positions are walked in the memory order of `out`; y (and r, when it follows y's order) go through shared memory
-// when their order differs.
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q, int nj) {
-  extern __shared__ float sh[];   // [2][T*V] staging (y, r)
+// positions are walked in the memory order of `out`; y / r kept in the other order go through shared memory.
+// BN_U samples are in flight per thread.
+template <int NJ>
+__global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q) {
+  extern __shared__ float sh[];   // [2][BN_U][T*V] staging (y, r)
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
   const bool y_stage = !same_order(q.y, q.out);
   const bool r_stage = q.r.p && !same_order(q.r, q.out);
   const float slope = q.prelu ? __ldg(q.prelu) : 1.f;
-  int tt[BN_MAXJ], vv[BN_MAXJ];
-  float sc[BN_MAXJ], sf[BN_MAXJ];
+  float* shy = sh;
+  float* shr = sh + BN_U * TV;
+  int tt[NJ], vv[NJ];
+  float sc[NJ], sf[NJ];
 #pragma unroll
-  for (int i = 0; i < BN_MAXJ; ++i) {
+  for (int i = 0; i < NJ; ++i) {
     tt[i] = -1;
     vv[i] = 0;
     sc[i] = sf[i] = 0.f;
-    if (i < nj) {
-      int j = threadIdx.x + i * blockDim.x;
-      if (j < TV) {
-        decode_pos(q.out, j, T, V, tt[i], vv[i]);
-        const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-        const float g = __ldg(q.gamma + pi), is = q.save_invstd[pi], mu = q.save_mean[pi];
-        sc[i] = g * is;
-        sf[i] = __ldg(q.beta + pi) - mu * g * is;
-      }
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < TV) {
+      decode_pos(q.out, j, T, V, tt[i], vv[i]);
+      const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
+      const float g = __ldg(q.gamma + pi), is = q.save_invstd[pi], mu = q.save_mean[pi];
+      sc[i] = g * is;
+      sf[i] = __ldg(q.beta + pi) - mu * g * is;
     }
   }
-  for (int n = n0; n < n1; ++n) {
+  for (int n = n0; n < n1; n += BN_U) {
     if (y_stage || r_stage) {
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < BN_MAXJ; ++i) {
-        if (i < nj) {
-          int j = threadIdx.x + i * blockDim.x;
-          if (j < TV) {
-            int t, v;
-            if (y_stage) {
-              decode_pos(q.y, j, T, V, t, v);
-              sh[t * V + v] = __ldg(q.y.p + vix(q.y, n, c, t, v));
-            }
-            if (r_stage) {
-              decode_pos(q.r, j, T, V, t, v);
-              sh[TV + t * V + v] = __ldg(q.r.p + vix(q.r, n, c, t, v));
-            }
-          }
-        }
-      }
+      if (y_stage) stage_planes<NJ>(q.y, c, n, n1, T, V, shy, TV);
+      if (r_stage) stage_planes<NJ>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < BN_MAXJ; ++i) {
-      if (i < nj && tt[i] >= 0) {
-        const int t = tt[i], v = vv[i];
-        float yv = y_stage ? sh[t * V + v] : __ldg(q.y.p + vix(q.y, n, c, t, v));
-        float pre = fmaf(yv, sc[i], sf[i]);
-        if (q.r.p) pre += r_stage ? sh[TV + t * V + v] : __ldg(q.r.p + vix(q.r, n, c, t, v));
-        float a = pre > 0.f ? pre : slope * pre;
-        if (q.mask) a *= __ldg(q.mask + (((long long)n * q.C + c) * T + t) * V + v);
-        q.out.p[vix(q.out, n, c, t, v)] = a;
+    for (int i = 0; i < NJ; ++i) {
+      if (tt[i] >= 0) {
+        const int t = tt[i], v = vv[i], e = t * V + v;
+        float yv[BN_U], rv[BN_U], mv[BN_U];
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          const bool ok = n + u < n1;
+          yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
+          rv[u] = !q.r.p ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
+          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          if (n + u < n1) {
+            const float pre = fmaf(yv[u], sc[i], sf[i]) + rv[u];
+            const float a = pre > 0.f ? pre : slope * pre;
+            q.out.p[vix(q.out, n + u, c, t, v)] = a * mv[u];
+          }
+        }
       }
     }
   }
@@ -226,14 +252,13 @@ struct BnBwdP {
 };
 
 // d(pre-activation) at one element; also returns xhat and the PReLU-slope contribution
-__device__ __forceinline__ float bn_gpre(const BnBwdP& q, int n, int c, int t, int v, float yv, float rv, float gv,
-                                         float mu, float is, float g, float b, float slope, float& xhat,
-                                         float& gslope) {
+__device__ __forceinline__ float bn_gpre(bool has_prelu, float yv, float rv, float gv, float mv, float mu, float is,
+                                         float g, float b, float slope, float& xhat, float& gslope) {
   xhat = (yv - mu) * is;
-  if (q.mask) gv *= __ldg(q.mask + (((long long)n * q.C + c) * q.T + t) * q.V + v);
+  gv *= mv;
   gslope = 0.f;
-  if (q.prelu) {
-    float pre = fmaf(xhat, g, b) + rv;
+  if (has_prelu) {
+    const float pre = fmaf(xhat, g, b) + rv;
     if (pre <= 0.f) {
       gslope = gv * pre;
       gv *= slope;
@@ -242,78 +267,75 @@ __device__ __forceinline__ float bn_gpre(const BnBwdP& q, int n, int c, int t, i
   return gv;
 }
 
-// pass 1: per-(c,v) sums of gpre and gpre*xhat, PReLU slope gradient.  Positions in gout's memory order; y / r are
-// staged through shared memory when they are kept in the other order.
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q, int nj) {
-  extern __shared__ float sh[];   // [2][T*V]
+// pass 1: per-(c,v) sums of gpre and gpre*xhat, PReLU slope gradient.  Positions in gout's memory order.
+template <int NJ>
+__global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q) {
+  extern __shared__ float sh[];   // [2][BN_U][T*V]
   __shared__ float red[32];
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
+  const bool has_prelu = q.prelu != nullptr;
+  const bool use_r = q.r.p && has_prelu;
   const bool y_stage = !same_order(q.y, q.gout);
-  const bool r_stage = q.r.p && q.prelu && !same_order(q.r, q.gout);
-  const float slope = q.prelu ? __ldg(q.prelu) : 1.f;
-  int tt[BN_MAXJ], vv[BN_MAXJ];
-  float mu[BN_MAXJ], is[BN_MAXJ], g[BN_MAXJ], b[BN_MAXJ], a1[BN_MAXJ], a2[BN_MAXJ];
+  const bool r_stage = use_r && !same_order(q.r, q.gout);
+  const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
+  float* shy = sh;
+  float* shr = sh + BN_U * TV;
+  int tt[NJ], vv[NJ];
+  float mu[NJ], is[NJ], g[NJ], b[NJ], a1[NJ], a2[NJ];
   float gsl = 0.f;
 #pragma unroll
-  for (int i = 0; i < BN_MAXJ; ++i) {
+  for (int i = 0; i < NJ; ++i) {
     tt[i] = -1;
     vv[i] = 0;
     mu[i] = is[i] = g[i] = b[i] = a1[i] = a2[i] = 0.f;
-    if (i < nj) {
-      int j = threadIdx.x + i * blockDim.x;
-      if (j < TV) {
-        decode_pos(q.gout, j, T, V, tt[i], vv[i]);
-        const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-        mu[i] = __ldg(q.save_mean + pi);
-        is[i] = __ldg(q.save_invstd + pi);
-        g[i] = __ldg(q.gamma + pi);
-        b[i] = __ldg(q.beta + pi);
-      }
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < TV) {
+      decode_pos(q.gout, j, T, V, tt[i], vv[i]);
+      const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
+      mu[i] = __ldg(q.save_mean + pi);
+      is[i] = __ldg(q.save_invstd + pi);
+      g[i] = __ldg(q.gamma + pi);
+      b[i] = __ldg(q.beta + pi);
     }
   }
-  for (int n = n0; n < n1; ++n) {
+  for (int n = n0; n < n1; n += BN_U) {
     if (y_stage || r_stage) {
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < BN_MAXJ; ++i) {
-        if (i < nj) {
-          int j = threadIdx.x + i * blockDim.x;
-          if (j < TV) {
-            int t, v;
-            if (y_stage) {
-              decode_pos(q.y, j, T, V, t, v);
-              sh[t * V + v] = __ldg(q.y.p + vix(q.y, n, c, t, v));
-            }
-            if (r_stage) {
-              decode_pos(q.r, j, T, V, t, v);
-              sh[TV + t * V + v] = __ldg(q.r.p + vix(q.r, n, c, t, v));
-            }
-          }
-        }
-      }
+      if (y_stage) stage_planes<NJ>(q.y, c, n, n1, T, V, shy, TV);
+      if (r_stage) stage_planes<NJ>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < BN_MAXJ; ++i) {
-      if (i < nj && tt[i] >= 0) {
-        const int t = tt[i], v = vv[i];
-        float yv = y_stage ? sh[t * V + v] : __ldg(q.y.p + vix(q.y, n, c, t, v));
-        float rv = 0.f;
-        if (q.r.p && q.prelu) rv = r_stage ? sh[TV + t * V + v] : __ldg(q.r.p + vix(q.r, n, c, t, v));
-        float gv = __ldg(q.gout.p + vix(q.gout, n, c, t, v));
-        float xhat, gs;
-        float gp = bn_gpre(q, n, c, t, v, yv, rv, gv, mu[i], is[i], g[i], b[i], slope, xhat, gs);
-        a1[i] += gp;
-        a2[i] = fmaf(gp, xhat, a2[i]);
-        gsl += gs;
+    for (int i = 0; i < NJ; ++i) {
+      if (tt[i] >= 0) {
+        const int t = tt[i], v = vv[i], e = t * V + v;
+        float yv[BN_U], rv[BN_U], gv[BN_U], mv[BN_U];
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          const bool ok = n + u < n1;
+          yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
+          rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
+          gv[u] = ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, t, v)) : 0.f;
+          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          if (n + u < n1) {
+            float xhat, gs;
+            const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
+            a1[i] += gp;
+            a2[i] = fmaf(gp, xhat, a2[i]);
+            gsl += gs;
+          }
+        }
       }
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < BN_MAXJ; ++i) {
-    if (i < nj && tt[i] >= 0) {
+  for (int i = 0; i < NJ; ++i) {
+    if (tt[i] >= 0) {
       sh[tt[i] * V + vv[i]] = a1[i];
       sh[TV + tt[i] * V + vv[i]] = a2[i];
     }
@@ -358,93 +380,108 @@ __global__ void bn_bwd_finalize_kernel(BnBwdP q) {
 }
 
 // pass 2: gy (and gr).  Positions in gy's memory order (= y's: gy is allocated like y).
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q, int nj) {
-  extern __shared__ float sh[];   // [3][T*V]: gout, r staging; gr transposition
+template <int NJ>
+__global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) {
+  extern __shared__ float sh[];   // [3][BN_U][T*V]: gout, r staging; gr transposition
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
+  const bool has_prelu = q.prelu != nullptr;
+  const bool use_r = q.r.p && has_prelu;
   const bool g_stage = !same_order(q.gout, q.gy);
-  const bool r_stage = q.r.p && q.prelu && !same_order(q.r, q.gy);
+  const bool r_stage = use_r && !same_order(q.r, q.gy);
   const bool gr_stage = q.gr.p && !same_order(q.gr, q.gy);
-  const float slope = q.prelu ? __ldg(q.prelu) : 1.f;
+  const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
   const float icnt = 1.0f / ((float)q.N * (float)T);
-  int tt[BN_MAXJ], vv[BN_MAXJ];
-  float mu[BN_MAXJ], is[BN_MAXJ], g[BN_MAXJ], b[BN_MAXJ], k1[BN_MAXJ], k2[BN_MAXJ];
+  float* shg = sh;
+  float* shr = sh + BN_U * TV;
+  float* sho = sh + 2 * BN_U * TV;
+  int tt[NJ], vv[NJ];
+  float mu[NJ], is[NJ], g[NJ], b[NJ], k1[NJ], k2[NJ];
 #pragma unroll
-  for (int i = 0; i < BN_MAXJ; ++i) {
+  for (int i = 0; i < NJ; ++i) {
     tt[i] = -1;
     vv[i] = 0;
     mu[i] = is[i] = g[i] = b[i] = k1[i] = k2[i] = 0.f;
-    if (i < nj) {
-      int j = threadIdx.x + i * blockDim.x;
-      if (j < TV) {
-        decode_pos(q.gy, j, T, V, tt[i], vv[i]);
-        const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-        mu[i] = __ldg(q.save_mean + pi);
-        is[i] = __ldg(q.save_invstd + pi);
-        g[i] = __ldg(q.gamma + pi);
-        b[i] = __ldg(q.beta + pi);
-        if (q.training) {
-          k1[i] = q.gbeta[pi] * icnt;
-          k2[i] = q.ggamma[pi] * icnt;
-        }
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < TV) {
+      decode_pos(q.gy, j, T, V, tt[i], vv[i]);
+      const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
+      mu[i] = __ldg(q.save_mean + pi);
+      is[i] = __ldg(q.save_invstd + pi);
+      g[i] = __ldg(q.gamma + pi);
+      b[i] = __ldg(q.beta + pi);
+      if (q.training) {
+        k1[i] = q.gbeta[pi] * icnt;
+        k2[i] = q.ggamma[pi] * icnt;
       }
     }
   }
-  for (int n = n0; n < n1; ++n) {
+  for (int n = n0; n < n1; n += BN_U) {
     if (g_stage || r_stage || gr_stage) {
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < BN_MAXJ; ++i) {
-        if (i < nj) {
-          int j = threadIdx.x + i * blockDim.x;
-          if (j < TV) {
-            int t, v;
-            if (g_stage) {
-              decode_pos(q.gout, j, T, V, t, v);
-              sh[t * V + v] = __ldg(q.gout.p + vix(q.gout, n, c, t, v));
-            }
-            if (r_stage) {
-              decode_pos(q.r, j, T, V, t, v);
-              sh[TV + t * V + v] = __ldg(q.r.p + vix(q.r, n, c, t, v));
-            }
-          }
-        }
-      }
+      if (g_stage) stage_planes<NJ>(q.gout, c, n, n1, T, V, shg, TV);
+      if (r_stage) stage_planes<NJ>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < BN_MAXJ; ++i) {
-      if (i < nj && tt[i] >= 0) {
-        const int t = tt[i], v = vv[i];
-        float yv = __ldg(q.y.p + vix(q.y, n, c, t, v));
-        float rv = 0.f;
-        if (q.r.p && q.prelu) rv = r_stage ? sh[TV + t * V + v] : __ldg(q.r.p + vix(q.r, n, c, t, v));
-        float gv = g_stage ? sh[t * V + v] : __ldg(q.gout.p + vix(q.gout, n, c, t, v));
-        float xhat, gs;
-        float gp = bn_gpre(q, n, c, t, v, yv, rv, gv, mu[i], is[i], g[i], b[i], slope, xhat, gs);
-        q.gy.p[vix(q.gy, n, c, t, v)] = g[i] * is[i] * (gp - k1[i] - xhat * k2[i]);
-        if (q.gr.p) {
-          if (gr_stage) sh[2 * TV + t * V + v] = gp;
-          else q.gr.p[vix(q.gr, n, c, t, v)] = gp;
+    for (int i = 0; i < NJ; ++i) {
+      if (tt[i] >= 0) {
+        const int t = tt[i], v = vv[i], e = t * V + v;
+        float yv[BN_U], rv[BN_U], gv[BN_U], mv[BN_U];
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          const bool ok = n + u < n1;
+          yv[u] = ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f;
+          rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
+          gv[u] = g_stage ? shg[u * TV + e] : (ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, t, v)) : 0.f);
+          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          if (n + u < n1) {
+            float xhat, gs;
+            const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
+            q.gy.p[vix(q.gy, n + u, c, t, v)] = g[i] * is[i] * (gp - k1[i] - xhat * k2[i]);
+            if (q.gr.p) {
+              if (gr_stage) sho[u * TV + e] = gp;
+              else q.gr.p[vix(q.gr, n + u, c, t, v)] = gp;
+            }
+          }
         }
       }
     }
     if (gr_stage) {
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < BN_MAXJ; ++i) {
-        if (i < nj) {
-          int j = threadIdx.x + i * blockDim.x;
-          if (j < TV) {
-            int t, v;
-            decode_pos(q.gr, j, T, V, t, v);
-            q.gr.p[vix(q.gr, n, c, t, v)] = sh[2 * TV + t * V + v];
-          }
+      for (int i = 0; i < NJ; ++i) {
+        const int j = threadIdx.x + i * blockDim.x;
+        if (j < TV) {
+          int t, v;
+          decode_pos(q.gr, j, T, V, t, v);
+#pragma unroll
+          for (int u = 0; u < BN_U; ++u)
+            if (n + u < n1) q.gr.p[vix(q.gr, n + u, c, t, v)] = sho[u * TV + t * V + v];
         }
       }
     }
   }
 }
+
+#define DSTD_BN_DISPATCH(kern, nj, grid, threads, smem, st, q)          \
+  do {                                                                  \
+    if ((smem) > 48 * 1024) {                                           \
+      ensure_max_smem((const void*)kern<1>);                            \
+      ensure_max_smem((const void*)kern<2>);                            \
+      ensure_max_smem((const void*)kern<4>);                            \
+      ensure_max_smem((const void*)kern<8>);                            \
+    }                                                                   \
+    switch (nj) {                                                       \
+      case 1: kern<1><<<grid, threads, smem, st>>>(q); break;           \
+      case 2: kern<2><<<grid, threads, smem, st>>>(q); break;           \
+      case 4: kern<4><<<grid, threads, smem, st>>>(q); break;           \
+      default: kern<8><<<grid, threads, smem, st>>>(q); break;          \
+    }                                                                   \
+  } while (0)
 
 }  // namespace dstd
 
@@ -484,9 +521,10 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
   q.part = ar.take<float>((size_t)q.S * q.C * q.V * 2);
   BnGeom g = bn_geom(q.T, q.V);
   const size_t sm2 = (size_t)2 * q.T * q.V * sizeof(float);
+  const size_t smu = sm2 * BN_U;
   const int cv = q.C * q.V;
   if (q.training) {
-    bn_stats_kernel<<<dim3(q.C, q.S), g.threads, sm2, st>>>(q, g.nj);
+    DSTD_BN_DISPATCH(bn_stats_kernel, g.nj, dim3(q.C, q.S), g.threads, sm2, st, q);
     count_launch();
     DSTD_LAUNCH_CHECK("bn_stats");
     bn_finalize_kernel<<<cdiv(cv, 128), 128, 0, st>>>(q);
@@ -497,7 +535,7 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
     count_launch();
     DSTD_LAUNCH_CHECK("bn_eval_stats");
   }
-  bn_apply_kernel<<<dim3(q.C, q.S), g.threads, sm2, st>>>(q, g.nj);
+  DSTD_BN_DISPATCH(bn_apply_kernel, g.nj, dim3(q.C, q.S), g.threads, smu, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_apply");
   return DSTD_OK;
@@ -528,13 +566,13 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   q.part_p = ar.take<float>((size_t)q.S * q.C);
   BnGeom g = bn_geom(q.T, q.V);
   const size_t tv = (size_t)q.T * q.V * sizeof(float);
-  bn_bwd_reduce_kernel<<<dim3(q.C, q.S), g.threads, 2 * tv, st>>>(q, g.nj);
+  DSTD_BN_DISPATCH(bn_bwd_reduce_kernel, g.nj, dim3(q.C, q.S), g.threads, 2 * BN_U * tv, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_reduce");
   bn_bwd_finalize_kernel<<<cdiv(q.C * q.V, 256), 256, 0, st>>>(q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_finalize");
-  bn_bwd_apply_kernel<<<dim3(q.C, q.S), g.threads, 3 * tv, st>>>(q, g.nj);
+  DSTD_BN_DISPATCH(bn_bwd_apply_kernel, g.nj, dim3(q.C, q.S), g.threads, 3 * BN_U * tv, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_apply");
   return DSTD_OK;

@@ -276,3 +276,127 @@ int launch_reduce(const ReduceParams& q, cudaStream_t st) {
 }
 
 }  // namespace dstd
+
+// ================================================================================= mproj backward
+// Backward of the 4*nb-row reduction convs (conv_m1 / conv_m2 of every branch, model/dstdgcn.py:82) in one pass over x:
+//   gx[c][g]  += sum_j wm[j][c] gm[j][g]                  (read-modify-write of the aggregation part of gx)
+//   gwm[j][c] += sum_g gm[j][g] [x;1][c][g]               (register accumulators, one partial per CTA)
+// Memory bound by design: x and gm are read once, gx is read and written once.
+namespace dstd {
+
+constexpr int MP_TP = 256;        // columns per tile (one per thread)
+constexpr int MP_LD = MP_TP + 4;  // (LD/4) odd: float4 reads along g with lane = channel are conflict free
+constexpr int MP_CG = 5;          // channel groups of 64 -> Cin + 1 <= 320
+
+__global__ void __launch_bounds__(256, 2) mproj_bwd_kernel(MprojBwdParams q) {
+  extern __shared__ __align__(16) float smem[];
+  const int Cin = q.Cin, C1 = Cin + 1, J = q.J, PK = q.P * q.K;
+  float* xs = smem;                    // [C1][MP_LD]
+  float* gms = xs + C1 * MP_LD;        // [8][MP_LD]
+  float* wmT = gms + 8 * MP_LD;        // [Cin][8]   wm transposed, zero padded to 8 rows
+  const int tid = threadIdx.x;
+  for (int i = tid; i < Cin * 8; i += 256) {
+    int c = i >> 3, j = i & 7;
+    wmT[i] = j < J ? __ldg(q.wm + (long long)j * C1 + c) : 0.f;
+  }
+  float acc[MP_CG][2];
+#pragma unroll
+  for (int a = 0; a < MP_CG; ++a) acc[a][0] = acc[a][1] = 0.f;
+  const int cl = tid & 63, jg = tid >> 6;   // phase 2: channel (+64 a), rows (2 jg, 2 jg + 1)
+  const long long ntiles = (q.G + MP_TP - 1) / MP_TP;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long g = tile * MP_TP + tid;
+    const bool ok = g < q.G;
+    long long ox = 0, og = 0, om = 0;
+    if (ok) {
+      const int n = (int)(g / PK);
+      const int rem = (int)(g - (long long)n * PK);
+      const int p = rem / q.K, k = rem - p * q.K;
+      ox = vix(q.x, n, 0, p, k);
+      og = vix(q.gx, n, 0, p, k);
+      om = (long long)n * J * PK + rem;
+    }
+    float gm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gm[j] = (ok && j < J) ? __ldg(q.gm + om + (long long)j * PK) : 0.f;
+    __syncthreads();   // previous tile's phase 2 done (also orders the wmT staging)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gms[j * MP_LD + tid] = gm[j];
+    // phase 1: gx update + stage x, 4 channels in flight
+    for (int c0 = 0; c0 < Cin; c0 += 4) {
+      float xv[4], gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool cok = ok && c0 + u < Cin;
+        xv[u] = cok ? __ldg(q.x.p + ox + (long long)(c0 + u) * q.x.sc) : 0.f;
+        gv[u] = cok ? q.gx.p[og + (long long)(c0 + u) * q.gx.sc] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c0 + u < Cin) {
+          const float4 wa = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8 + 4);
+          float s = gv[u];
+          s = fmaf(wa.x, gm[0], s); s = fmaf(wa.y, gm[1], s); s = fmaf(wa.z, gm[2], s); s = fmaf(wa.w, gm[3], s);
+          s = fmaf(wb.x, gm[4], s); s = fmaf(wb.y, gm[5], s); s = fmaf(wb.z, gm[6], s); s = fmaf(wb.w, gm[7], s);
+          if (ok) q.gx.p[og + (long long)(c0 + u) * q.gx.sc] = s;
+          xs[(c0 + u) * MP_LD + tid] = xv[u];
+        }
+      }
+    }
+    xs[Cin * MP_LD + tid] = ok ? 1.0f : 0.f;   // ones row (bias gradients)
+    __syncthreads();
+    // phase 2: gwm[j][c] += sum_g gm[j][g] x[c][g]
+#pragma unroll
+    for (int a = 0; a < MP_CG; ++a) {
+      const int c = cl + 64 * a;
+      if (c < C1) {
+        const float* xr = xs + c * MP_LD;
+        const float* g0 = gms + (2 * jg) * MP_LD;
+        const float* g1 = g0 + MP_LD;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+        for (int g4 = 0; g4 < MP_TP; g4 += 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(xr + g4);
+          const float4 a0 = *reinterpret_cast<const float4*>(g0 + g4);
+          const float4 a1 = *reinterpret_cast<const float4*>(g1 + g4);
+          s0 = fmaf(a0.x, xv.x, s0); s0 = fmaf(a0.y, xv.y, s0); s0 = fmaf(a0.z, xv.z, s0); s0 = fmaf(a0.w, xv.w, s0);
+          s1 = fmaf(a1.x, xv.x, s1); s1 = fmaf(a1.y, xv.y, s1); s1 = fmaf(a1.z, xv.z, s1); s1 = fmaf(a1.w, xv.w, s1);
+        }
+        acc[a][0] += s0;
+        acc[a][1] += s1;
+      }
+    }
+  }
+  float* dst = q.partial + (long long)blockIdx.x * J * C1;
+#pragma unroll
+  for (int a = 0; a < MP_CG; ++a) {
+    const int c = cl + 64 * a;
+    if (c < C1) {
+      if (2 * jg < J) dst[(long long)(2 * jg) * C1 + c] = acc[a][0];
+      if (2 * jg + 1 < J) dst[(long long)(2 * jg + 1) * C1 + c] = acc[a][1];
+    }
+  }
+}
+
+bool mproj_bwd_supported(int Cin, int J) {
+  return J <= 8 && Cin + 1 <= 64 * MP_CG &&
+         ((size_t)(Cin + 1 + 8) * MP_LD + (size_t)Cin * 8) * sizeof(float) <= (size_t)MAX_DYN_SMEM;
+}
+
+int mproj_bwd_ctas(long long G) {
+  long long t = (G + MP_TP - 1) / MP_TP;
+  return (int)(t < 296 ? t : 296);
+}
+
+int launch_mproj_bwd(const MprojBwdParams& q, cudaStream_t st) {
+  DSTD_REQUIRE(mproj_bwd_supported(q.Cin, q.J), DSTD_ERR_UNSUPPORTED, "mproj_bwd: Cin=%d J=%d outside limits", q.Cin, q.J);
+  size_t smem = ((size_t)(q.Cin + 1 + 8) * MP_LD + (size_t)q.Cin * 8) * sizeof(float);
+  if (smem > 48 * 1024) ensure_max_smem((const void*)mproj_bwd_kernel);
+  mproj_bwd_kernel<<<mproj_bwd_ctas(q.G), 256, smem, st>>>(q);
+  count_launch();
+  return check_launch("mproj_bwd");
+}
+
+}  // namespace dstd

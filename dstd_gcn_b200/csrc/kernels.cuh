@@ -36,6 +36,19 @@ struct WgradParams {
 int wgrad_splits(long long G);
 int launch_wgrad(WgradParams& q, cudaStream_t st);   // fills q.S (number of partials actually written)
 
+struct MprojBwdParams {
+  int Cin, J, P, K;    // J = 4 * nb rows of [conv_m1; conv_m2] per branch
+  long long G;         // columns = N*P*K
+  View4 x;             // [N,Cin,P,K]
+  View4 gx;            // [N,Cin,P,K] read-modify-write
+  const float* gm;     // dense [N,J,P,K]
+  const float* wm;     // [J][Cin+1]
+  float* partial;      // [ctas][J][Cin+1]
+};
+bool mproj_bwd_supported(int Cin, int J);
+int mproj_bwd_ctas(long long G);
+int launch_mproj_bwd(const MprojBwdParams& q, cudaStream_t st);
+
 struct ReduceSeg {
   const float* src;    // partial k, element (r, c) at src[k*sstride + r*src_ld + c]
   int S;

@@ -91,7 +91,8 @@ def test_gc_unit_abi(case):
     assert out.stride() == out_r.stride()
     assert max_abs(m, m_r) < 2e-5
     assert max_abs(pd, pd_r) < 5e-5
-    assert max_abs(xa, xa_r) < 1e-4 * max(1.0, float(xa_r.abs().max()) / 10)
+    if xa.numel():     # only kept for shapes whose backward cannot recompute it on chip (dstd_gc_needs_xa)
+        assert max_abs(xa, xa_r) < 1e-4 * max(1.0, float(xa_r.abs().max()) / 10)
     assert max_abs(out, out_r) < 1e-4 * max(1.0, float(out_r.abs().max()) / 10)
 
     gout = unit_input(g, n, cout, p, k, layout)
