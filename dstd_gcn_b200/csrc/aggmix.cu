@@ -30,40 +30,57 @@ __global__ void __launch_bounds__(256) aggmix_fwd_kernel(AggMixParams q) {
   float* xms = xs + ((Cin * XS_LD + 3) & ~3);         // [nb][PCH][K][KP]
   float* xas = xms + nb * PCH * K * KP;               // [C1][XA_LD]
   float* ws = xas + ((C1 * XA_LD + 3) & ~3);          // [nb*C1][CoutP]
+  float* aeff = ws + nb * C1 * CoutP;                 // [nb][K*K]
+  // raw dynamic adjacency [nb][PCH][K*K]: dead after staging, so it borrows the xa tile when that is large enough
+  float* pdr = (C1 * XA_LD >= nb * PCH * KK) ? xas : aeff + ((nb * KK + 3) & ~3);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.y, p0 = blockIdx.x * PCH;
   const int pv = min(PCH, P - p0);                    // valid frames in this chunk
   const int npos = pv * K;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
 
-  // ---- stage: weights (already transposed + padded by the pack kernel), adjacency chunk, input chunk
+  // ---- stage with cp.async (every copy of a thread in flight at once): packed weights, input chunk, raw dynamic
+  //      adjacency; the static adjacency A*W + R is formed meanwhile, then xm = alpha*pd + A_eff from shared memory
   {
-    const float4* src = reinterpret_cast<const float4*>(q.wcatT);
-    float4* dst = reinterpret_cast<float4*>(ws);
     const int n4 = nb * C1 * CoutP / 4;
-    for (int i = tid; i < n4; i += 256) dst[i] = __ldg(src + i);
-  }
-  for (int i = tid; i < nb * PCH * K * KP; i += 256) {
-    int w = i % KP, t = i / KP;
-    int v = t % K;
-    t /= K;
-    int l = t % PCH, b = t / PCH;
-    float val = 0.f;
-    if (w < K && l < pv) {
-      int e = q.adj_t ? (w * K + v) : (v * K + w);
+    for (int i = tid; i < n4; i += 256) cp_async16(ws + 4 * i, q.wcatT + 4 * i);
+    int poff[TN];
+#pragma unroll
+    for (int i = 0; i < TN; ++i) {
+      const int j = lane + 32 * i;
+      const int l = j / K, k = j - l * K;
+      poff[i] = j < npos ? (int)(l * q.x.sp + k * q.x.sk) : -1;
+    }
+    const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
+    for (int c = warp; c < Cin; c += 8) {
+#pragma unroll
+      for (int i = 0; i < TN; ++i)
+        if (poff[i] >= 0) cp_async4(xs + c * XS_LD + lane + 32 * i, xb + (long long)c * q.x.sc + poff[i], true);
+    }
+    for (int b = 0; b < nb; ++b) {
+      const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
+      for (int i = tid; i < pv * KK; i += 256) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+    }
+    for (int i = tid; i < nb * KK; i += 256) {
+      const int b = i / KK, e = i - b * KK;
       float a = __ldg(q.adj[b] + e);
       if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + e);
       if (q.adj_r[b]) a += __ldg(q.adj_r[b] + e);
-      val = fmaf(alpha, __ldg(q.pd + ((long long)(n * nb + b) * P + p0 + l) * KK + e), a);
+      aeff[i] = a;
     }
-    xms[i] = val;
-  }
-  {
-    const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
-    for (int i = tid; i < Cin * npos; i += 256) {
-      int c = i / npos, j = i - c * npos;
-      int l = j / K, k = j - l * K;
-      xs[c * XS_LD + j] = __ldg(xb + (long long)c * q.x.sc + (long long)l * q.x.sp + (long long)k * q.x.sk);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int i = tid; i < nb * PCH * K * KP; i += 256) {
+      int w = i % KP, t = i / KP;
+      int v = t % K;
+      t /= K;
+      int l = t % PCH, b = t / PCH;
+      float val = 0.f;
+      if (w < K && l < pv) {
+        const int e = q.adj_t ? (w * K + v) : (v * K + w);
+        val = fmaf(alpha, pdr[(b * PCH + l) * KK + e], aeff[b * KK + e]);
+      }
+      xms[i] = val;
     }
   }
   __syncthreads();
@@ -185,7 +202,8 @@ struct AggMixGeom {
 static size_t aggmix_smem(int Cin, int CoutP, int K, int nb, int WH, int TN, int PCH) {
   const int C1 = Cin + 1, KP = 2 * WH, XS_LD = (PCH * K) | 1, XA_LD = 32 * TN + 1;
   size_t f = (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * PCH * K * KP + (size_t)((C1 * XA_LD + 3) & ~3) +
-             (size_t)nb * C1 * CoutP;
+             (size_t)nb * C1 * CoutP + (size_t)((nb * K * K + 3) & ~3) +
+             (C1 * XA_LD >= nb * PCH * K * K ? 0 : (size_t)nb * PCH * K * K);
   return f * sizeof(float);
 }
 

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
   float* xmT = xms + nb * PCH * K * KP2;    // [nb][PCH][K][KP2]   xmu[l][w][v]
   float* wfB = xmT + nb * PCH * K * KP2;    // [nb][Cout][CinP]
   float* bfs = wfB + nb * Cout * CinP;      // [nb][Cout]
+  float* aeff = bfs + ((nb * Cout + 3) & ~3);   // [nb][K*K]    static adjacency A*W + R
+  float* pdr = aeff + ((nb * KK + 3) & ~3);     // [nb][PCH][K*K] raw dynamic adjacency of the current item
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
   const int nchunk = (P + PCH - 1) / PCH;
@@ -45,6 +47,13 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
     wfB[i] = c < Cin ? __ldg(q.w_f[b] + (long long)o * Cin + c) : 0.f;
   }
   for (int i = tid; i < nb * Cout; i += 256) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
+  for (int i = tid; i < nb * KK; i += 256) {
+    const int b = i / KK, e = i - b * KK;
+    float a = __ldg(q.adj[b] + e);
+    if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + e);
+    if (q.adj_r[b]) a += __ldg(q.adj_r[b] + e);
+    aeff[i] = a;
+  }
 
   // persistent weight-gradient accumulators: warp = 8 output channels, lane = input channels (lane, lane+32)
   float accw[DSTD_MAX_BRANCH][8][2];
@@ -62,25 +71,42 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
     const int pv = min(PCH, P - p0);
     __syncthreads();   // previous item fully consumed (also orders the one-time weight staging)
 
-    // ---- stage x (+ ones row), gout, adjacency (both orientations)
+    // ---- stage x (+ ones row), gout and the raw dynamic adjacency with cp.async (all copies of a thread in flight at
+    //      once), then build xmu = alpha*pd + A_eff in both orientations from shared memory
     {
+      int poff_x[TN], poff_g[TN];
+      bool pok[TN];
+#pragma unroll
+      for (int i = 0; i < TN; ++i) {
+        const int pos = lane + 32 * i;
+        const int l = pos / KP, k = pos - l * KP;
+        pok[i] = pos < npos_pad && l < pv && k < K;
+        poff_x[i] = pok[i] ? (int)(l * q.x.sp + k * q.x.sk) : 0;
+        poff_g[i] = pok[i] ? (int)(l * q.gout.sp + k * q.gout.sk) : 0;
+      }
       const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
-      for (int i = tid; i < C1 * npos_pad; i += 256) {
-        int c = i / npos_pad, j = i - c * npos_pad;
-        int l = j / KP, k = j - l * KP;
-        float v = 0.f;
-        if (l < pv && k < K)
-          v = c < Cin ? __ldg(xb + (long long)c * q.x.sc + (long long)l * q.x.sp + (long long)k * q.x.sk) : 1.0f;
-        xs[c * LD + j] = v;
+      for (int c = warp; c < Cin; c += 8) {
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+          if (lane + 32 * i < npos_pad) cp_async4(xs + c * LD + lane + 32 * i, xb + (long long)c * q.x.sc + poff_x[i], pok[i]);
       }
       const float* gb = q.gout.p + (long long)n * q.gout.sn + (long long)p0 * q.gout.sp;
-      for (int i = tid; i < Cout * npos_pad; i += 256) {
-        int c = i / npos_pad, j = i - c * npos_pad;
-        int l = j / KP, k = j - l * KP;
-        float v = 0.f;
-        if (l < pv && k < K) v = __ldg(gb + (long long)c * q.gout.sc + (long long)l * q.gout.sp + (long long)k * q.gout.sk);
-        gos[c * LD + j] = v;
+      for (int c = warp; c < Cout; c += 8) {
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+          if (lane + 32 * i < npos_pad) cp_async4(gos + c * LD + lane + 32 * i, gb + (long long)c * q.gout.sc + poff_g[i], pok[i]);
       }
+      for (int b = 0; b < nb; ++b) {
+        const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
+        for (int i = tid; i < pv * KK; i += 256) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+      }
+      if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+          if (lane + 32 * i < npos_pad) xs[Cin * LD + lane + 32 * i] = pok[i] ? 1.0f : 0.f;
+      }
+      cp_async_wait_all();
+      __syncthreads();
       for (int i = tid; i < nb * PCH * K * KP2; i += 256) {
         int w = i % KP2, t = i / KP2;
         int v = t % K;
@@ -88,15 +114,11 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
         int l = t % PCH, b = t / PCH;
         float val = 0.f, valT = 0.f;
         if (w < K && l < pv) {
-          // xmu[v][w] = xm[v][w] (or xm[w][v] when adj_t);  row (v) of xms, row (v as "w") of xmT
-          const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0 + l) * KK;
-          int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
-          int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
-          float a = __ldg(q.adj[b] + e), aT = __ldg(q.adj[b] + eT);
-          if (q.adj_w[b]) { a *= __ldg(q.adj_w[b] + e); aT *= __ldg(q.adj_w[b] + eT); }
-          if (q.adj_r[b]) { a += __ldg(q.adj_r[b] + e); aT += __ldg(q.adj_r[b] + eT); }
-          val = fmaf(alpha, __ldg(pdl + e), a);
-          valT = fmaf(alpha, __ldg(pdl + eT), aT);
+          const int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
+          const int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
+          const float* pr = pdr + (b * PCH + l) * KK;
+          val = fmaf(alpha, pr[e], aeff[b * KK + e]);
+          valT = fmaf(alpha, pr[eT], aeff[b * KK + eT]);
         }
         xms[i] = val;
         xmT[i] = valT;
@@ -384,7 +406,7 @@ static bool aggmix_bwd_geom(int Cin, int Cout, int P, int K, int nb, AggMixBwdGe
     int ld = npad + 4;
     if ((ld / 4) % 2 == 0) ld += 4;
     size_t f = (size_t)(3 * C1 + Cout + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * Cout * g.CinP +
-               (size_t)nb * Cout + 16;
+               (size_t)nb * Cout + (size_t)nb * K * K * (pch + 1) + 32;
     if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 512) {
       g.PCH = pch;
       g.LD = ld;

@@ -65,15 +65,34 @@ __device__ __forceinline__ long long vix(const View4& v, int n, int c, int p, in
   return (long long)n * v.sn + (long long)c * v.sc + (long long)p * v.sp + (long long)k * v.sk;
 }
 
-// tanh with ~3e-7 absolute error: 1 - 2/(exp(2x)+1) through ex2.approx / rcp (two MUFU ops).
-// (tanh.approx.f32 is ~5e-4 relative: too coarse for the 1e-4 parity budget once scaled by conv_rm.)
+// tanh of the pairwise differences.  Default: CUDA's tanhf (polynomial below 0.55, ex2/rcp above; <= 2 ulp), measured
+// at 7.0 results/clk/SM on B200 against 7.9 for the bare ex2+rcp form (tools/microbench.cu).  The bare form
+// 1 - 2/(exp(2x)+1) has a ~1.2e-7 ABSOLUTE error, i.e. a large relative error on the small differences that dominate
+// here; on the full-depth model that error, amplified by the cancellation in bias-like gradients, cost 3-5x in gradient
+// parity (tools/diag_fullsize.py), so it is opt-in (-DDSTD_FAST_TANH).  tanh.approx.f32 (5e-4 relative) is out of the
+// question for the 1e-4 parity budget.
 __device__ __forceinline__ float fast_tanh(float x) {
-#ifdef DSTD_ACCURATE_TANH
-  return tanhf(x);
-#else
+#ifdef DSTD_FAST_TANH
   float e = exp2f(x * 2.885390081777927f);  // exp(2x); ex2.approx, saturates to inf / 0
   return 1.0f - __fdividef(2.0f, e + 1.0f);
+#else
+  return tanhf(x);
 #endif
+}
+
+// ---- cp.async (LDGSTS): fire-and-forget global -> shared copies; a staging loop issues all of them back to back, so the
+// memory-level parallelism is the number of copies per thread, not 1.  valid == false zero-fills the destination.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -43,6 +43,20 @@ __global__ void __launch_bounds__(256) k_tanh(float* out, float a) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__global__ void __launch_bounds__(256) k_tanhf(float* out, float a) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = threadIdx.x * 0.001f + i * a;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = tanhf(r[i] + a);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += r[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) k_tanh_approx(float* out, float a) {
   float r[8];
 #pragma unroll
@@ -155,6 +169,8 @@ int main() {
   ms = time_ms([&] { k_tanh<<<blocks, 256>>>(out, 0.01f); });
   double nt = (double)blocks * 256.0 * ITERS * 8;
   printf("tanh (ex2+rcp)   : %8.3f ms  %7.2f Gtanh/s   (%.2f /clk/SM @1.9GHz)\n", ms, nt / ms * 1e-6, nt / (ms * 1e-3) / sms / 1.9e9);
+  ms = time_ms([&] { k_tanhf<<<blocks, 256>>>(out, 0.01f); });
+  printf("tanhf (libdevice): %8.3f ms  %7.2f Gtanh/s   (%.2f /clk/SM @1.9GHz)\n", ms, nt / ms * 1e-6, nt / (ms * 1e-3) / sms / 1.9e9);
   ms = time_ms([&] { k_tanh_approx<<<blocks, 256>>>(out, 0.01f); });
   printf("tanh.approx      : %8.3f ms  %7.2f Gtanh/s   (%.2f /clk/SM @1.9GHz)\n", ms, nt / ms * 1e-6, nt / (ms * 1e-3) / sms / 1.9e9);
   ms = time_ms([&] { k_mma_tf32<<<blocks, 256>>>(out, 0x3f800000u); });
