@@ -32,9 +32,9 @@ class FlatParams:
     def __init__(self, model: torch.nn.Module):
         self.named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
         total = sum(p.numel() for _, p in self.named)
-        dev = self.named[0][1].device
-        self.param = torch.empty(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        dev, dt = self.named[0][1].device, self.named[0][1].dtype     # fp32 in the product; fp64 only in CPU tests
+        self.param = torch.empty(total, dtype=dt, device=dev)
+        self.grad = torch.zeros(total, dtype=dt, device=dev)
         self.slices = {}
         off = 0
         for k, p in self.named:
@@ -50,7 +50,7 @@ class FlatParams:
         """autograd accumulates in place into the views; re-attach them if something detached a ``.grad``."""
         for k, p in self.named:
             off, n, shape = self.slices[k]
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + self.grad.element_size() * off:
                 p.grad = self.grad[off:off + n].view(shape)
 
 
@@ -75,7 +75,7 @@ class TrainStep:
         dev = self.flat.param.device
         # learning rate and step count also live on the device so that a captured CUDA graph of the step stays valid
         # across steps and StepLR updates (engine/prediction.py:193-196,310)
-        self.lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)
+        self.lr_dev = torch.full((1,), self.lr, dtype=self.flat.param.dtype, device=dev)
         self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.graph = None
         self._static = None
