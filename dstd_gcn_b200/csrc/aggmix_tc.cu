@@ -1,0 +1,382 @@
+// Fused adjacency aggregation + channel mix, forward, with the channel contraction on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM) -- the sm_100a path of model/dstdgcn.py:81 + :87/:93 (+ :150/:161/:248).
+//
+// Persistent CTAs (one per SM).  The conv_f weights of every branch stay resident in shared memory for the life of the
+// CTA, already split into TF32 "hi" and "lo" parts and laid out as UMMA K-major core matrices by the pack kernel.
+// Per work item (sample n, chunk of PCH frames):
+//   1. cp.async staging of the x chunk and the raw dynamic adjacency; xm = alpha*pd + A_eff formed in shared memory
+//   2. per branch b: CUDA-core aggregation  xa_b[c][pos] = sum_v x[c][l,v] xm_b[l][v][w]  written straight into the UMMA
+//      A-operand tile (positions = M rows, channels = K, hi/lo split on the fly), then ONE elected thread issues
+//      3 x (KD/8) tcgen05.mma (hi*hi + hi*lo + lo*hi: 3xTF32 error compensation, ~1e-6 relative, needed for the 1e-4
+//      parity budget) accumulating D[pos][o] over both branches in TMEM; completion through tcgen05.commit -> mbarrier
+//   3. epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> (+ skip) -> coalesced stores of out[o][pos]
+// Tile format (validated in isolation by tools/umma_test.cu): K-major, no swizzle, 8 x 16 B core matrices,
+//   element (row r, k) at (r/8)*SBO + (k/4)*LBO + (r%8)*16 + (k%4)*4 bytes with LBO = 144 B (not 128: the 16-byte skew
+//   makes the lane = channel stores of the aggregation bank-conflict free) and SBO = (KD/4)*LBO.
+#include <stdlib.h>
+
+#include "kernels.cuh"
+
+namespace dstd {
+
+constexpr int TC_LBO_F = 36;   // floats between K-adjacent core matrices (144 B)
+
+__host__ __device__ __forceinline__ int tc_off(int r, int k, int sbo_f) {
+  return (r >> 3) * sbo_f + (k >> 2) * TC_LBO_F + ((r & 7) << 2) + (k & 3);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  return d;                 // layout type 0: no swizzle
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(acc)
+      : "memory");
+}
+
+// bounded wait (a malformed pipeline must fail loudly, not hang the GPU)
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int it = 0; it < (1 << 22) && !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+  return done != 0;
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));   // round to nearest: |lo| <= 2^-11 |x|
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
+template <int WH>
+__global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, int KD, int NP, int tmem_cols, int* err_flag) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KP = 2 * WH;
+  const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, Cout = q.Cout, nb = q.nb, PCH = q.PCH;
+  const int sbo_f = (KD / 4) * TC_LBO_F;
+  // rows (positions) actually written; the M = 128 descriptor reads on into the following buffers for the unused rows,
+  // which only produces D rows nobody loads
+  const int a_tile_f = ((PCH * K + 7) / 8) * sbo_f;
+  const int b_tile_f = (NP / 8) * sbo_f;             // NP rows (output channels, padded to 16)
+  const int npos_max = PCH * K;
+  const int XS_LD = npos_max | 1;
+  float* a_hi = smem;                                // UMMA A operand tiles
+  float* a_lo = a_hi + a_tile_f;
+  float* b_img = a_lo + a_tile_f;                    // [nb][hi|lo][b_tile_f]   resident weights
+  float* xs = b_img + nb * 2 * b_tile_f;             // [Cin][XS_LD]
+  float* xms = xs + ((Cin * XS_LD + 3) & ~3);        // [nb][PCH][K][KP]
+  float* aeff = xms + nb * PCH * K * KP;             // [nb][K*K]
+  float* pdr = aeff + ((nb * KK + 3) & ~3);          // [nb][PCH][K*K]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(pdr + ((nb * PCH * KK + 3) & ~3));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
+  const int nchunk = (P + PCH - 1) / PCH;
+  const long long nitems = (long long)q.N * nchunk;
+
+  // ---- once per CTA: resident weights, static adjacency, zeroed A tiles (pad rows of K must read as 0), TMEM, mbarrier
+  {
+    const int n4 = nb * 2 * b_tile_f / 4;
+    for (int i = tid; i < n4; i += 256) cp_async16(b_img + 4 * i, q.wtc + 4 * i);
+    for (int i = tid; i < 2 * a_tile_f; i += 256) a_hi[i] = 0.f;
+    for (int i = tid; i < nb * KK; i += 256) {
+      const int b = i / KK, e = i - b * KK;
+      float a = __ldg(q.adj[b] + e);
+      if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + e);
+      if (q.adj_r[b]) a += __ldg(q.adj_r[b] + e);
+      aeff[i] = a;
+    }
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    cp_async_wait_all();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t lbo_b = TC_LBO_F * 4, sbo_b = (uint32_t)sbo_f * 4;
+  uint32_t phase = 0;
+  bool ok = true;
+
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int n = (int)(item / nchunk), p0 = (int)(item - (long long)n * nchunk) * PCH;
+    const int pv = min(PCH, P - p0);
+    const int npos = pv * K;
+
+    // ---- 1. stage x chunk + raw dynamic adjacency
+    {
+      constexpr int TNS = 4;   // 128 position slots
+      int poff[TNS];
+#pragma unroll
+      for (int i = 0; i < TNS; ++i) {
+        const int j = lane + 32 * i;
+        const int l = j / K, k = j - l * K;
+        poff[i] = j < npos ? (int)(l * q.x.sp + k * q.x.sk) : -1;
+      }
+      const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
+      for (int c = warp; c < Cin; c += 8) {
+#pragma unroll
+        for (int i = 0; i < TNS; ++i)
+          if (poff[i] >= 0) cp_async4(xs + c * XS_LD + lane + 32 * i, xb + (long long)c * q.x.sc + poff[i], true);
+      }
+      for (int b = 0; b < nb; ++b) {
+        const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
+        for (int i = tid; i < pv * KK; i += 256) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      for (int i = tid; i < nb * PCH * K * KP; i += 256) {
+        int w = i % KP, t = i / KP;
+        int v = t % K;
+        t /= K;
+        int l = t % PCH, b = t / PCH;
+        float val = 0.f;
+        if (w < K && l < pv) {
+          const int e = q.adj_t ? (w * K + v) : (v * K + w);
+          val = fmaf(alpha, pdr[(b * PCH + l) * KK + e], aeff[b * KK + e]);
+        }
+        xms[i] = val;
+      }
+      __syncthreads();
+    }
+
+    // ---- 2. per branch: aggregation into the UMMA A tile, then the tensor-core channel mix
+    for (int b = 0; b < nb; ++b) {
+      for (int it = warp; it < 2 * pv; it += 8) {
+        const int l = it >> 1, half = it & 1;
+        const float* xm_l = xms + ((b * PCH + l) * K) * KP + half * WH;
+        for (int cg = 0; cg < Cin; cg += 64) {
+          const int c0 = cg + lane, c1 = c0 + 32;
+          const float* x0p = xs + min(c0, Cin - 1) * XS_LD + l * K;
+          const float* x1p = xs + min(c1, Cin - 1) * XS_LD + l * K;
+          float a0[WH], a1[WH];
+#pragma unroll
+          for (int j = 0; j < WH; ++j) a0[j] = a1[j] = 0.f;
+          for (int v = 0; v < K; ++v) {
+            const float x0 = x0p[v], x1 = x1p[v];
+            const float4* r4 = reinterpret_cast<const float4*>(xm_l + v * KP);
+#pragma unroll
+            for (int j4 = 0; j4 < WH / 4; ++j4) {
+              const float4 m = r4[j4];
+              a0[j4 * 4 + 0] = fmaf(x0, m.x, a0[j4 * 4 + 0]);
+              a0[j4 * 4 + 1] = fmaf(x0, m.y, a0[j4 * 4 + 1]);
+              a0[j4 * 4 + 2] = fmaf(x0, m.z, a0[j4 * 4 + 2]);
+              a0[j4 * 4 + 3] = fmaf(x0, m.w, a0[j4 * 4 + 3]);
+              a1[j4 * 4 + 0] = fmaf(x1, m.x, a1[j4 * 4 + 0]);
+              a1[j4 * 4 + 1] = fmaf(x1, m.y, a1[j4 * 4 + 1]);
+              a1[j4 * 4 + 2] = fmaf(x1, m.z, a1[j4 * 4 + 2]);
+              a1[j4 * 4 + 3] = fmaf(x1, m.w, a1[j4 * 4 + 3]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < WH; ++j) {
+            const int w = half * WH + j;
+            if (w < K) {
+              const int pos = l * K + w;
+              float hi, lo;
+              if (c0 < Cin) {
+                split_tf32(a0[j], hi, lo);
+                const int o = tc_off(pos, c0, sbo_f);
+                a_hi[o] = hi;
+                a_lo[o] = lo;
+              }
+              if (c1 < Cin) {
+                split_tf32(a1[j], hi, lo);
+                const int o = tc_off(pos, c1, sbo_f);
+                a_hi[o] = hi;
+                a_lo[o] = lo;
+              }
+            }
+          }
+        }
+        if (lane < WH && half * WH + lane < K) {   // ones row (K index Cin): column sums of xm carry the conv_f bias
+          float s = 0.f;
+          for (int v = 0; v < K; ++v) s += xm_l[v * KP + lane];
+          float hi, lo;
+          split_tf32(s, hi, lo);
+          const int o = tc_off(l * K + half * WH + lane, Cin, sbo_f);
+          a_hi[o] = hi;
+          a_lo[o] = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dah = tc_desc(smem_u32(a_hi), lbo_b, sbo_b), dal = tc_desc(smem_u32(a_lo), lbo_b, sbo_b);
+        const uint64_t dbh = tc_desc(smem_u32(b_img + (b * 2 + 0) * b_tile_f), lbo_b, sbo_b);
+        const uint64_t dbl = tc_desc(smem_u32(b_img + (b * 2 + 1) * b_tile_f), lbo_b, sbo_b);
+        for (int ks = 0; ks < KD / 8; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * 2 * lbo_b) >> 4);   // 8 K-elements = two core matrices
+          umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, (b > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+          umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+                     : "memory");
+      }
+      // the A tile is rewritten by the next branch / item and TMEM is read by the epilogue only after the MMAs retire
+      ok = mbar_wait(smem_u32(mbar), phase) && ok;
+      phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    // ---- 3. epilogue: TMEM -> registers -> out (+ skip).  warp w: lanes 32 (w%4) .. +31 (positions), columns 32 (w/4) ..
+    {
+      const int pos = (warp & 3) * 32 + lane;
+      const int l = pos / K, k = pos - l * K;
+      const bool pok = pos < npos;
+      const long long off_o = (long long)n * q.out.sn + (long long)(p0 + l) * q.out.sp + (long long)k * q.out.sk;
+      const long long off_s = q.skip.p ? (long long)n * q.skip.sn + (long long)(p0 + l) * q.skip.sp + (long long)k * q.skip.sk : 0;
+      for (int col0 = (warp >> 2) * 32; col0 < NP; col0 += 64) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (pok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int o = col0 + j;
+            if (o < Cout) {
+              float v = ok ? __uint_as_float(r[j]) : __int_as_float(0x7fc00000);   // a stalled pipeline must be loud
+              if (q.skip.p) v += __ldg(q.skip.p + off_s + (long long)o * q.skip.sc);
+              q.out.p[off_o + (long long)o * q.out.sc] = v;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();   // TMEM drained and xs / xms / pdr free before the next item
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+  }
+  if (!ok && tid == 0) atomicExch(err_flag, 1);
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ weight image for the tensor path
+// wtc[b][hi|lo][tc_off(o, j)]: conv_f weights (+ bias in K row Cin) of branch b as UMMA K-major core matrices, TF32 split
+__global__ void pack_tc_zero_kernel(float* wtc, int nwords) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) wtc[i] = 0.f;
+}
+__global__ void pack_tc_scatter_kernel(PackParams q, float* wtc, int KD, int NP) {
+  const int sbo_f = (KD / 4) * TC_LBO_F, tile = (NP / 8) * sbo_f;
+  const int total = q.nb * q.Cout * (q.Cin + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % (q.Cin + 1);
+    int t = i / (q.Cin + 1);
+    const int o = t % q.Cout, b = t / q.Cout;
+    const float w = j < q.Cin ? __ldg(q.w_f[b] + (long long)o * q.Cin + j) : __ldg(q.b_f[b] + o);
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(w));
+    const float hi = __uint_as_float(h);
+    const int off = tc_off(o, j, sbo_f);
+    wtc[(b * 2 + 0) * tile + off] = hi;
+    wtc[(b * 2 + 1) * tile + off] = w - hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ geometry / launch
+struct TcGeom {
+  int WH, PCH, KD, NP, tmem_cols;
+  size_t smem, wtc_floats;
+};
+
+static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g) {
+  if (K > 40 || K < 1 || Cin > 64 || Cout > 64) return false;
+  g.WH = K <= 24 ? 12 : K <= 32 ? 16 : 20;
+  g.KD = (Cin + 1 + 7) / 8 * 8;
+  g.NP = (Cout + 15) / 16 * 16;
+  g.tmem_cols = g.NP <= 32 ? 32 : 64;
+  const int KP = 2 * g.WH, sbo_f = (g.KD / 4) * TC_LBO_F;
+  g.wtc_floats = (size_t)nb * 2 * (g.NP / 8) * sbo_f;
+  for (int pch = 128 / K; pch >= 1; --pch) {
+    if (pch > P && pch > 1) continue;
+    const int XS_LD = (pch * K) | 1;
+    size_t f = (size_t)2 * ((pch * K + 7) / 8) * sbo_f + g.wtc_floats + (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * pch * K * KP +
+               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + 8;
+    if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 256) {
+      g.PCH = pch;
+      g.smem = f * sizeof(float);
+      return true;
+    }
+  }
+  return false;
+}
+
+bool aggmix_tc_supported(int Cin, int Cout, int P, int K, int nb) {
+  static const bool disabled = getenv("DSTD_DISABLE_TC") != nullptr;
+  if (disabled) return false;
+  TcGeom g;
+  return tc_geom(Cin, Cout, P, K, nb, g);
+}
+
+size_t aggmix_tc_ws_floats(int Cin, int Cout, int P, int K, int nb) {
+  TcGeom g;
+  if (!tc_geom(Cin, Cout, P, K, nb, g)) return 0;
+  return g.wtc_floats + 4;   // + error flag
+}
+
+int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cudaStream_t st) {
+  TcGeom g;
+  DSTD_REQUIRE(tc_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g), DSTD_ERR_UNSUPPORTED, "aggmix_fwd_tc: shape outside limits");
+  int* err_flag = reinterpret_cast<int*>(wtc_ws + g.wtc_floats);
+  const int nw = (int)g.wtc_floats + 4;   // image + error flag
+  pack_tc_zero_kernel<<<min(cdiv(nw, 256), 64), 256, 0, st>>>(wtc_ws, nw);
+  pack_tc_scatter_kernel<<<min(cdiv(q.nb * q.Cout * (q.Cin + 1), 256), 64), 256, 0, st>>>(pk, wtc_ws, g.KD, g.NP);
+  count_launch(2);
+  DSTD_LAUNCH_CHECK("pack_tc");
+  q.PCH = g.PCH;
+  q.CoutP = g.NP;
+  q.wtc = wtc_ws;
+  const long long items = (long long)q.N * cdiv(q.P, g.PCH);
+  const int ctas = (int)(items < 148 ? items : 148);
+#define DSTD_AMTC(WH_)                                                                      \
+  if (g.WH == WH_) {                                                                        \
+    auto kern = aggmix_fwd_tc_kernel<WH_>;                                                  \
+    ensure_max_smem((const void*)kern);                                                     \
+    kern<<<ctas, 256, g.smem, st>>>(q, g.KD, g.NP, g.tmem_cols, err_flag);                  \
+  }
+  DSTD_AMTC(12) DSTD_AMTC(16) DSTD_AMTC(20)
+#undef DSTD_AMTC
+  count_launch();
+  return check_launch("aggmix_fwd_tc");
+}
+
+}  // namespace dstd

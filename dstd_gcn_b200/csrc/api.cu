@@ -45,9 +45,9 @@ struct GcWs {
   int S1, S2;
 };
 
-static size_t gc_fwd_ws(int Cin, int Cout, int nb) {
+static size_t gc_fwd_ws(int Cin, int Cout, int nb, int P = 40, int K = 40) {
   return arena_need({(size_t)Cout * nb * (Cin + 1) * 4, (size_t)4 * nb * (Cin + 1) * 4,
-                     (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4});
+                     (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4, aggmix_tc_ws_floats(Cin, Cout, P, K, nb) * 4});
 }
 static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   const size_t C1 = Cin + 1, G = (size_t)N * P * K;
@@ -111,8 +111,8 @@ extern "C" int dstd_gc_needs_xa(int Cin, int Cout, int P, int K, int nb) {
   return (aggmix_supported(Cin, Cout, P, K, nb) && aggmix_bwd_supported(Cin, Cout, P, K, nb)) ? 0 : 1;
 }
 extern "C" size_t dstd_gc_fwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb) {
-  (void)N; (void)P; (void)K;
-  return gc_fwd_ws(Cin, Cout, nb);
+  (void)N;
+  return gc_fwd_ws(Cin, Cout, nb, P, K);
 }
 extern "C" size_t dstd_gc_bwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb) {
   return gc_bwd_ws(N, Cin, Cout, P, K, nb);
@@ -124,8 +124,8 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_forward");
   if (rc) return rc;
   DSTD_REQUIRE(a->x.ptr && a->out.ptr && a->m && a->pd, DSTD_ERR_BAD_ARG, "gc_forward: null tensor");
-  DSTD_REQUIRE(a->ws && a->ws_bytes >= gc_fwd_ws(a->Cin, a->Cout, a->nb), DSTD_ERR_WORKSPACE,
-               "gc_forward: workspace too small (%zu < %zu)", a->ws_bytes, gc_fwd_ws(a->Cin, a->Cout, a->nb));
+  DSTD_REQUIRE(a->ws && a->ws_bytes >= gc_fwd_ws(a->Cin, a->Cout, a->nb, a->P, a->K), DSTD_ERR_WORKSPACE,
+               "gc_forward: workspace too small (%zu < %zu)", a->ws_bytes, gc_fwd_ws(a->Cin, a->Cout, a->nb, a->P, a->K));
   cudaStream_t st = (cudaStream_t)stream;
   const int N = a->N, Cin = a->Cin, Cout = a->Cout, P = a->P, K = a->K, nb = a->nb, C1 = Cin + 1;
   const long long G = (long long)N * P * K;
@@ -133,6 +133,8 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   float* wcat = ar.take<float>((size_t)Cout * nb * C1);
   float* wm = ar.take<float>((size_t)4 * nb * C1);
   float* wcatT = ar.take<float>((size_t)nb * C1 * ((Cout + 7) / 8 * 8));
+  float* wtc = ar.take<float>(aggmix_tc_ws_floats(Cin, Cout, P, K, nb));
+  const bool use_tc = !a->xa && aggmix_tc_supported(Cin, Cout, P, K, nb);   // tcgen05 channel mix
   const bool fused = aggmix_supported(Cin, Cout, P, K, nb);
 
   PackParams pk;
@@ -170,7 +172,9 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
       am.adj[b] = s.adj; am.adj_w[b] = s.adj_w; am.adj_r[b] = s.adj_r;
     }
     am.wcatT = wcatT;
+    am.wtc = nullptr;
     am.xa = a->xa;
+    if (use_tc) return launch_aggmix_fwd_tc(am, pk, wtc, st);
     return launch_aggmix_fwd(am, st);
   }
   DSTD_REQUIRE(a->xa, DSTD_ERR_BAD_ARG, "gc_forward: the unfused path needs the xa buffer");

@@ -125,10 +125,16 @@ struct AggMixParams {
   const float* adj_w[DSTD_MAX_BRANCH];
   const float* adj_r[DSTD_MAX_BRANCH];
   const float* wcatT;  // [nb*(Cin+1)][CoutP] from the pack kernel
+  const float* wtc;    // tensor-core path: UMMA weight image (filled by launch_aggmix_fwd_tc)
   float* xa;           // optional [N,nb,Cin+1,P,K]
 };
 int launch_aggmix_fwd(AggMixParams q, cudaStream_t st);
 bool aggmix_supported(int Cin, int Cout, int P, int K, int nb);
+// tcgen05 variant (aggmix_tc.cu)
+struct PackParams;
+bool aggmix_tc_supported(int Cin, int Cout, int P, int K, int nb);
+size_t aggmix_tc_ws_floats(int Cin, int Cout, int P, int K, int nb);
+int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cudaStream_t st);
 
 // ------------------------------------------------------------------ aggmix_bwd.cu
 struct AggMixBwdParams {
