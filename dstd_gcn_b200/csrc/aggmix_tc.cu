@@ -331,6 +331,9 @@ static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g) {
     const int XS_LD = (pch * K) | 1;
     size_t f = (size_t)2 * ((pch * K + 7) / 8) * sbo_f + g.wtc_floats + (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * pch * K * KP +
                (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + 8;
+    // the M = 128 descriptors read 16 row groups from each A tile: keep that window inside the allocation
+    const size_t a_window = (size_t)((pch * K + 7) / 8) * sbo_f + (size_t)16 * sbo_f + 64;
+    if (f < a_window) f = a_window;
     if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 256) {
       g.PCH = pch;
       g.smem = f * sizeof(float);
