@@ -326,10 +326,13 @@ def main():
             line["cpu_baseline"] = {"value": v_cpu, "unit": "samples/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_baseline_steps} engine steps of batch {cb} (same workload "
                                               f"shape, fp32), {sec:.2f} s/step"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # no collective and no communicator teardown at exit: a rank that is done leaves immediately (rank 0 may still be
+        # timing the CPU baseline), and NCCL teardown after graph replays has been seen to block on this stack
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

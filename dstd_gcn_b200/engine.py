@@ -78,6 +78,7 @@ class TrainStep:
         self.lr_dev = torch.full((1,), self.lr, dtype=self.flat.param.dtype, device=dev)
         self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.graph = None
+        self._graph_has_update = False
         self._static = None
         self._static_loss = None
 
@@ -103,8 +104,8 @@ class TrainStep:
         loss.backward()
         return loss.detach()
 
-    def _eager(self, inputs, inputs_inv, targets):
-        loss = self.loss_and_grads(inputs, inputs_inv, targets)
+    def _finish_step(self):
+        """All-reduce of the flat gradient bucket (the path's only collective), optional clip, fused Adam."""
         if self.world > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
         gscale = 1.0 / self.world
@@ -115,6 +116,10 @@ class TrainStep:
         torch.ops.dstd_b200.adam_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr,
                                       self.betas[0], self.betas[1], self.eps, self.weight_decay, gscale, 0,
                                       self.lr_dev, self.step_dev)
+
+    def _eager(self, inputs, inputs_inv, targets):
+        loss = self.loss_and_grads(inputs, inputs_inv, targets)
+        self._finish_step()
         return loss
 
     def __call__(self, inputs, inputs_inv, targets):
@@ -124,6 +129,8 @@ class TrainStep:
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
             self.graph.replay()
+            if not self._graph_has_update:
+                self._finish_step()
             return self._static_loss
         return self._eager(inputs, inputs_inv, targets)
 
@@ -157,9 +164,15 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         self._restore(snap)
         torch.cuda.synchronize()
+        # single GPU: the whole step is one graph.  Data parallel: the graph ends after the backward pass and the
+        # NCCL all-reduce + Adam (3 launches) are issued eagerly behind it, so no collective is captured.
+        self._graph_has_update = self.world == 1
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._static_loss = self._eager(*self._static)
+            if self._graph_has_update:
+                self._static_loss = self._eager(*self._static)
+            else:
+                self._static_loss = self.loss_and_grads(*self._static)
         self._restore(snap)       # capture itself does not execute, but keep the invariant explicit
         self.graph = g
         return self
