@@ -15,10 +15,18 @@ namespace dstd {
 
 constexpr int BN_THREADS_MAX = 512;
 constexpr int BN_MAXJ = 8;       // positions per thread  -> T*V <= 4096
-constexpr int BN_U = 4;          // samples in flight per thread (memory-level parallelism)
+// samples in flight per thread (memory-level parallelism): 8 for the dataset shapes (T*V <= 1024), 4 beyond
+#define BN_U ((NJ) <= 2 ? 8 : 4)
+#define BN_UB ((NJ) <= 1 ? 8 : 4)
+static int bn_u(int nj) { return nj <= 2 ? 8 : 4; }
+static int bn_ub(int nj) { return nj <= 1 ? 8 : 4; }
 
-int bn_act_splits(int N) {
-  int s = (N + 7) / 8;            // ~8 samples per CTA
+int bn_act_splits(int N, int C) {
+  // ~600 CTAs (4 per SM) so that the per-thread set-up (parameter gathers, position decode) is amortised over as many
+  // samples as possible, but never fewer than 8 samples per CTA
+  int s = (600 + C - 1) / C;
+  const int smax = (N + 7) / 8;
+  if (s > smax) s = smax;
   if (s > 128) s = 128;
   if (s < 1) s = 1;
   return s;
@@ -67,9 +75,9 @@ struct BnFwdP {
 };
 
 // stage BN_U planes of `src` (walked in its own memory order, coalesced) into sh[u][t*V+v]
-template <int NJ>
+template <int NJ, int U>
 __device__ __forceinline__ void stage_planes(const View4& src, int c, int n, int n1, int T, int V, float* sh, int TV) {
-  float tmp[BN_U][NJ];
+  float tmp[U][NJ];
   int idx[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
@@ -81,14 +89,14 @@ __device__ __forceinline__ void stage_planes(const View4& src, int c, int n, int
       idx[i] = t * V + v;
       const float* p = src.p + (long long)n * src.sn + (long long)c * src.sc + pos_off(src, t, v);
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) tmp[u][i] = (n + u < n1) ? __ldg(p + (long long)u * src.sn) : 0.f;
+      for (int u = 0; u < U; ++u) tmp[u][i] = (n + u < n1) ? __ldg(p + (long long)u * src.sn) : 0.f;
     }
   }
 #pragma unroll
   for (int i = 0; i < NJ; ++i)
     if (idx[i] >= 0) {
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) sh[u * TV + idx[i]] = tmp[u][i];
+      for (int u = 0; u < U; ++u) sh[u * TV + idx[i]] = tmp[u][i];
     }
 }
 
@@ -212,8 +220,8 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q) {
   for (int n = n0; n < n1; n += BN_U) {
     if (y_stage || r_stage) {
       __syncthreads();
-      if (y_stage) stage_planes<NJ>(q.y, c, n, n1, T, V, shy, TV);
-      if (r_stage) stage_planes<NJ>(q.r, c, n, n1, T, V, shr, TV);
+      if (y_stage) stage_planes<NJ, BN_U>(q.y, c, n, n1, T, V, shy, TV);
+      if (r_stage) stage_planes<NJ, BN_U>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
     }
 #pragma unroll
@@ -270,7 +278,7 @@ __device__ __forceinline__ float bn_gpre(bool has_prelu, float yv, float rv, flo
 // pass 1: per-(c,v) sums of gpre and gpre*xhat, PReLU slope gradient.  Positions in gout's memory order.
 template <int NJ>
 __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q) {
-  extern __shared__ float sh[];   // [2][BN_U][T*V]
+  extern __shared__ float sh[];   // [2][BN_UB][T*V]
   __shared__ float red[32];
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q)
   const bool r_stage = use_r && !same_order(q.r, q.gout);
   const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
   float* shy = sh;
-  float* shr = sh + BN_U * TV;
+  float* shr = sh + BN_UB * TV;
   int tt[NJ], vv[NJ];
   float mu[NJ], is[NJ], g[NJ], b[NJ], a1[NJ], a2[NJ];
   float gsl = 0.f;
@@ -299,20 +307,20 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q)
       b[i] = __ldg(q.beta + pi);
     }
   }
-  for (int n = n0; n < n1; n += BN_U) {
+  for (int n = n0; n < n1; n += BN_UB) {
     if (y_stage || r_stage) {
       __syncthreads();
-      if (y_stage) stage_planes<NJ>(q.y, c, n, n1, T, V, shy, TV);
-      if (r_stage) stage_planes<NJ>(q.r, c, n, n1, T, V, shr, TV);
+      if (y_stage) stage_planes<NJ, BN_UB>(q.y, c, n, n1, T, V, shy, TV);
+      if (r_stage) stage_planes<NJ, BN_UB>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       if (tt[i] >= 0) {
         const int t = tt[i], v = vv[i], e = t * V + v;
-        float yv[BN_U], rv[BN_U], gv[BN_U], mv[BN_U];
+        float yv[BN_UB], rv[BN_UB], gv[BN_UB], mv[BN_UB];
 #pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
+        for (int u = 0; u < BN_UB; ++u) {
           const bool ok = n + u < n1;
           yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
           rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q)
           mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
         }
 #pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
+        for (int u = 0; u < BN_UB; ++u) {
           if (n + u < n1) {
             float xhat, gs;
             const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
@@ -382,7 +390,7 @@ __global__ void bn_bwd_finalize_kernel(BnBwdP q) {
 // pass 2: gy (and gr).  Positions in gy's memory order (= y's: gy is allocated like y).
 template <int NJ>
 __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) {
-  extern __shared__ float sh[];   // [3][BN_U][T*V]: gout, r staging; gr transposition
+  extern __shared__ float sh[];   // [3][BN_UB][T*V]: gout, r staging; gr transposition
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
   const bool has_prelu = q.prelu != nullptr;
@@ -393,8 +401,8 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
   const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
   const float icnt = 1.0f / ((float)q.N * (float)T);
   float* shg = sh;
-  float* shr = sh + BN_U * TV;
-  float* sho = sh + 2 * BN_U * TV;
+  float* shr = sh + BN_UB * TV;
+  float* sho = sh + 2 * BN_UB * TV;
   int tt[NJ], vv[NJ];
   float mu[NJ], is[NJ], g[NJ], b[NJ], k1[NJ], k2[NJ];
 #pragma unroll
@@ -416,20 +424,20 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
       }
     }
   }
-  for (int n = n0; n < n1; n += BN_U) {
+  for (int n = n0; n < n1; n += BN_UB) {
     if (g_stage || r_stage || gr_stage) {
       __syncthreads();
-      if (g_stage) stage_planes<NJ>(q.gout, c, n, n1, T, V, shg, TV);
-      if (r_stage) stage_planes<NJ>(q.r, c, n, n1, T, V, shr, TV);
+      if (g_stage) stage_planes<NJ, BN_UB>(q.gout, c, n, n1, T, V, shg, TV);
+      if (r_stage) stage_planes<NJ, BN_UB>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       if (tt[i] >= 0) {
         const int t = tt[i], v = vv[i], e = t * V + v;
-        float yv[BN_U], rv[BN_U], gv[BN_U], mv[BN_U];
+        float yv[BN_UB], rv[BN_UB], gv[BN_UB], mv[BN_UB];
 #pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
+        for (int u = 0; u < BN_UB; ++u) {
           const bool ok = n + u < n1;
           yv[u] = ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f;
           rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
           mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
         }
 #pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
+        for (int u = 0; u < BN_UB; ++u) {
           if (n + u < n1) {
             float xhat, gs;
             const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
           int t, v;
           decode_pos(q.gr, j, T, V, t, v);
 #pragma unroll
-          for (int u = 0; u < BN_U; ++u)
+          for (int u = 0; u < BN_UB; ++u)
             if (n + u < n1) q.gr.p[vix(q.gr, n + u, c, t, v)] = sho[u * TV + t * V + v];
         }
       }
@@ -489,7 +497,8 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
 using namespace dstd;
 
 extern "C" size_t dstd_bn_act_workspace_bytes(int N, int C, int T, int V) {
-  int S = bn_act_splits(N);
+  int S = (N + 7) / 8 > 128 ? 128 : (N + 7) / 8;   // upper bound of bn_act_splits
+  if (S < 1) S = 1;
   return arena_need({(size_t)S * C * V * 2 * sizeof(float), (size_t)S * C * sizeof(float)});
 }
 
@@ -509,7 +518,7 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
   BnFwdP q;
   q.N = a->N; q.C = a->C; q.T = a->T; q.V = a->V;
   q.vc_order = a->vc_order; q.training = a->training;
-  q.S = bn_act_splits(a->N);
+  q.S = bn_act_splits(a->N, a->C);
   q.eps = a->eps; q.momentum = a->momentum;
   q.y = mk(a->y); q.r = mk(a->r); q.out = mk(a->out);
   q.gamma = a->gamma; q.beta = a->beta;
@@ -521,7 +530,7 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
   q.part = ar.take<float>((size_t)q.S * q.C * q.V * 2);
   BnGeom g = bn_geom(q.T, q.V);
   const size_t sm2 = (size_t)2 * q.T * q.V * sizeof(float);
-  const size_t smu = sm2 * BN_U;
+  const size_t smu = sm2 * bn_u(g.nj);
   const int cv = q.C * q.V;
   if (q.training) {
     DSTD_BN_DISPATCH(bn_stats_kernel, g.nj, dim3(q.C, q.S), g.threads, sm2, st, q);
@@ -556,7 +565,7 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   BnBwdP q;
   q.N = a->N; q.C = a->C; q.T = a->T; q.V = a->V;
   q.vc_order = a->vc_order; q.training = a->training;
-  q.S = bn_act_splits(a->N);
+  q.S = bn_act_splits(a->N, a->C);
   q.y = mk(a->y); q.r = mk(a->r); q.gout = mk(a->gout); q.gy = mk(a->gy); q.gr = mk(a->gr);
   q.gamma = a->gamma; q.beta = a->beta; q.prelu = a->prelu; q.mask = a->mask;
   q.save_mean = a->save_mean; q.save_invstd = a->save_invstd;
@@ -566,13 +575,13 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   q.part_p = ar.take<float>((size_t)q.S * q.C);
   BnGeom g = bn_geom(q.T, q.V);
   const size_t tv = (size_t)q.T * q.V * sizeof(float);
-  DSTD_BN_DISPATCH(bn_bwd_reduce_kernel, g.nj, dim3(q.C, q.S), g.threads, 2 * BN_U * tv, st, q);
+  DSTD_BN_DISPATCH(bn_bwd_reduce_kernel, g.nj, dim3(q.C, q.S), g.threads, 2 * bn_ub(g.nj) * tv, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_reduce");
   bn_bwd_finalize_kernel<<<cdiv(q.C * q.V, 256), 256, 0, st>>>(q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_finalize");
-  DSTD_BN_DISPATCH(bn_bwd_apply_kernel, g.nj, dim3(q.C, q.S), g.threads, 3 * BN_U * tv, st, q);
+  DSTD_BN_DISPATCH(bn_bwd_apply_kernel, g.nj, dim3(q.C, q.S), g.threads, 3 * bn_ub(g.nj) * tv, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_apply");
   return DSTD_OK;

@@ -159,7 +159,7 @@ bool aggmix_bwd_supported(int Cin, int Cout, int P, int K, int nb);
 int aggmix_bwd_ctas(int N, int P, int K, int Cin, int Cout, int nb);
 
 // ------------------------------------------------------------------ bn_act.cu
-int bn_act_splits(int N);
+int bn_act_splits(int N, int C);
 
 // ------------------------------------------------------------------ misc.cu
 struct PackParams {
