@@ -7,7 +7,7 @@
 //   1. cp.async staging of the x chunk and the raw dynamic adjacency; xm = alpha*pd + A_eff formed in shared memory
 //   2. per branch b: CUDA-core aggregation  xa_b[c][pos] = sum_v x[c][l,v] xm_b[l][v][w]  written straight into the UMMA
 //      A-operand tile (positions = M rows, channels = K, hi/lo split on the fly), then ONE elected thread issues
-//      3 x (KD/8) tcgen05.mma (hi*hi + hi*lo + lo*hi: 3xTF32 error compensation, ~1e-6 relative, needed for the 1e-4
+//      4 x (KD/8) tcgen05.mma (hi*hi + hi*lo + lo*hi + lo*lo: split-TF32 error compensation, needed for the 1e-4
 //      parity budget) accumulating D[pos][o] over both branches in TMEM; completion through tcgen05.commit -> mbarrier
 //   3. epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> (+ skip) -> coalesced stores of out[o][pos]
 // Tile format (validated in isolation by tools/umma_test.cu): K-major, no swizzle, 8 x 16 B core matrices,
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
           umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, (b > 0 || ks > 0) ? 1u : 0u);
           umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
           umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+          umma_tf32(tmem_d, dal + adv, dbl + adv, idesc, 1u);   // lo*lo: the tensor pipe is idle anyway, keep the product exact
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
                      : "memory");

@@ -16,17 +16,14 @@ namespace dstd {
 constexpr int BN_THREADS_MAX = 512;
 constexpr int BN_MAXJ = 8;       // positions per thread  -> T*V <= 4096
 // samples in flight per thread (memory-level parallelism): 8 for the dataset shapes (T*V <= 1024), 4 beyond
-#define BN_U ((NJ) <= 2 ? 8 : 4)
+#define BN_U 4
 #define BN_UB ((NJ) <= 1 ? 8 : 4)
-static int bn_u(int nj) { return nj <= 2 ? 8 : 4; }
+static int bn_u(int nj) { (void)nj; return 4; }
 static int bn_ub(int nj) { return nj <= 1 ? 8 : 4; }
 
 int bn_act_splits(int N, int C) {
-  // ~600 CTAs (4 per SM) so that the per-thread set-up (parameter gathers, position decode) is amortised over as many
-  // samples as possible, but never fewer than 8 samples per CTA
-  int s = (600 + C - 1) / C;
-  const int smax = (N + 7) / 8;
-  if (s > smax) s = smax;
+  (void)C;
+  int s = (N + 7) / 8;            // ~8 samples per CTA (measured: fewer, longer CTAs are slower)
   if (s > 128) s = 128;
   if (s < 1) s = 1;
   return s;
@@ -202,19 +199,20 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q) {
   float* shy = sh;
   float* shr = sh + BN_U * TV;
   int tt[NJ], vv[NJ];
-  float sc[NJ], sf[NJ];
+  float sc[NJ], sf[NJ], sm[NJ];   // out = (y - mean) * (gamma * invstd) + beta  (centred first: no cancellation)
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     tt[i] = -1;
     vv[i] = 0;
-    sc[i] = sf[i] = 0.f;
+    sc[i] = sf[i] = sm[i] = 0.f;
     const int j = threadIdx.x + i * blockDim.x;
     if (j < TV) {
       decode_pos(q.out, j, T, V, tt[i], vv[i]);
       const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-      const float g = __ldg(q.gamma + pi), is = q.save_invstd[pi], mu = q.save_mean[pi];
+      const float g = __ldg(q.gamma + pi), is = q.save_invstd[pi];
+      sm[i] = q.save_mean[pi];
       sc[i] = g * is;
-      sf[i] = __ldg(q.beta + pi) - mu * g * is;
+      sf[i] = __ldg(q.beta + pi);
     }
   }
   for (int n = n0; n < n1; n += BN_U) {
@@ -239,7 +237,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q) {
 #pragma unroll
         for (int u = 0; u < BN_U; ++u) {
           if (n + u < n1) {
-            const float pre = fmaf(yv[u], sc[i], sf[i]) + rv[u];
+            const float pre = fmaf(yv[u] - sm[i], sc[i], sf[i]) + rv[u];
             const float a = pre > 0.f ? pre : slope * pre;
             q.out.p[vix(q.out, n + u, c, t, v)] = a * mv[u];
           }

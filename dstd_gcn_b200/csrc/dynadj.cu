@@ -136,7 +136,7 @@ bool dynadj_supported(int P, int K) {
   return bwd_geom(P, K).smem_floats * sizeof(float) <= 220 * 1024;
 }
 
-int dynadj_bwd_splits(int N) { return N < 148 ? N : 148; }   // x nb branches, 2 CTAs / SM: one wave
+int dynadj_bwd_splits(int N) { return N < 296 ? N : 296; }
 
 template <int TMA, int TNA>
 __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int RV, int ECP, int WLD) {

@@ -403,13 +403,26 @@ def test_full_size_model_vs_oracle(variant, layout, v, tin, tout):
     y.pow(2).mean().backward()
     assert rel_err(y, y64) < max(1e-4, 4 * rel_err(y32, y64))
     assert rel_err(xd.grad, gx64) < max(1e-3, 10 * rel_err(gx32, gx64))
+    # all parameter gradients together: relative L2 error within 4x of what fp32 torch arithmetic loses (or 5e-3)
+    num = den = num32 = 0.0
+    for k, p in md.named_parameters():
+        if p.grad is None:
+            continue
+        d = p.grad.double().cpu() - g64[k]
+        num += float((d * d).sum())
+        num32 += float(((g32[k].double() - g64[k]) ** 2).sum())
+        den += float((g64[k] ** 2).sum())
+    rel, rel32 = (num / den) ** 0.5, (num32 / den) ** 0.5
+    assert rel < max(5e-3, 4 * rel32), (rel, rel32)
+    # per tensor: bias-like gradients (plain sums of a zero-mean upstream gradient: PReLU slopes, alpha, conv_m biases,
+    # R_t) cancel by 1e3..1e4, so their relative error is that much larger than the error of the terms: 10 % of scale
     gmax = max(float(t.abs().max()) for t in g64.values())
     bad = []
     for k, p in md.named_parameters():
         if p.grad is None:
             continue
         e, e32, scale = max_abs(p.grad, g64[k]), max_abs(g32[k], g64[k]), float(g64[k].abs().max())
-        if e > max(30 * e32, 3e-2 * scale, 1e-6 * gmax):
+        if e > max(30 * e32, 1e-1 * scale, 1e-6 * gmax):
             bad.append((k, e, e32, scale))
     assert not bad, bad[:5]
 
