@@ -16,8 +16,10 @@
 
 namespace dstd {
 
+constexpr int AMB_NT = 512;   // 16 warps; the two channel GEMMs are split 2-way along their reduction dimension
+
 template <int KP, int TN>
-__global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
+__global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
   extern __shared__ __align__(16) float smem[];
   constexpr int WH = (KP / 2 + 3) / 4 * 4;   // half of a padded adjacency row, multiple of 4
   constexpr int KP2 = 2 * WH;
@@ -41,13 +43,13 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
   const long long nitems = (long long)q.N * nchunk;
 
   // ---- once per CTA: weights
-  for (int i = tid; i < nb * Cout * CinP; i += 256) {
+  for (int i = tid; i < nb * Cout * CinP; i += AMB_NT) {
     int c = i % CinP, t = i / CinP;
     int o = t % Cout, b = t / Cout;
     wfB[i] = c < Cin ? __ldg(q.w_f[b] + (long long)o * Cin + c) : 0.f;
   }
-  for (int i = tid; i < nb * Cout; i += 256) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
-  for (int i = tid; i < nb * KK; i += 256) {
+  for (int i = tid; i < nb * Cout; i += AMB_NT) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
+  for (int i = tid; i < nb * KK; i += AMB_NT) {
     const int b = i / KK, e = i - b * KK;
     float a = __ldg(q.adj[b] + e);
     if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + e);
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) accw[b][r][0] = accw[b][r][1] = 0.f;
   }
-  const int o0 = warp * 8;
+  const int o0 = (warp & 7) * 8;
 
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int n = (int)(item / nchunk), p0 = (int)(item - (long long)n * nchunk) * PCH;
@@ -85,20 +87,20 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
         poff_g[i] = pok[i] ? (int)(l * q.gout.sp + k * q.gout.sk) : 0;
       }
       const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
-      for (int c = warp; c < Cin; c += 8) {
+      for (int c = warp; c < Cin; c += AMB_NT / 32) {
 #pragma unroll
         for (int i = 0; i < TN; ++i)
           if (lane + 32 * i < npos_pad) cp_async4(xs + c * LD + lane + 32 * i, xb + (long long)c * q.x.sc + poff_x[i], pok[i]);
       }
       const float* gb = q.gout.p + (long long)n * q.gout.sn + (long long)p0 * q.gout.sp;
-      for (int c = warp; c < Cout; c += 8) {
+      for (int c = warp; c < Cout; c += AMB_NT / 32) {
 #pragma unroll
         for (int i = 0; i < TN; ++i)
           if (lane + 32 * i < npos_pad) cp_async4(gos + c * LD + lane + 32 * i, gb + (long long)c * q.gout.sc + poff_g[i], pok[i]);
       }
       for (int b = 0; b < nb; ++b) {
         const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
-        for (int i = tid; i < pv * KK; i += 256) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+        for (int i = tid; i < pv * KK; i += AMB_NT) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
       }
       if (warp == 0) {
 #pragma unroll
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
       }
       cp_async_wait_all();
       __syncthreads();
-      for (int i = tid; i < nb * PCH * K * KP2; i += 256) {
+      for (int i = tid; i < nb * PCH * K * KP2; i += AMB_NT) {
         int w = i % KP2, t = i / KP2;
         int v = t % K;
         t /= K;
@@ -129,61 +131,78 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
 #pragma unroll
     for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {   // unrolled: accw[b] must stay in registers
       if (b >= nb) break;
-      // ================= (a) gxa_b = wcat_b^T gout    (warp = 8 rows j, lane = positions)
-      for (int j0 = warp * 8; j0 < Cin; j0 += 64) {
+      // ================= (a) gxa_b = wcat_b^T gout    (warp = 8 rows j x half of the o range, lane = positions;
+      //                   the two halves are combined through gxas)
+      {
+        const int ks = warp >> 3, j0 = (warp & 7) * 8;
+        const int oh = (Cout + 1) >> 1, ob = ks * oh, oe = min(Cout, ob + oh);
+        const bool act = j0 < Cin;
         float acc[8][TN];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
           for (int i = 0; i < TN; ++i) acc[r][i] = 0.f;
-        const float* wrow = wfB + (b * Cout) * CinP + j0;
+        if (act) {
+          const float* wrow = wfB + (b * Cout) * CinP + j0;
 #pragma unroll 2
-        for (int o = 0; o < Cout; ++o) {
-          const float4 wa = *reinterpret_cast<const float4*>(wrow + o * CinP);
-          const float4 wb = *reinterpret_cast<const float4*>(wrow + o * CinP + 4);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-          float gv[TN];
+          for (int o = ob; o < oe; ++o) {
+            const float4 wa = *reinterpret_cast<const float4*>(wrow + o * CinP);
+            const float4 wb = *reinterpret_cast<const float4*>(wrow + o * CinP + 4);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            float gv[TN];
 #pragma unroll
-          for (int i = 0; i < TN; ++i) gv[i] = gos[o * LD + lane + 32 * i];
+            for (int i = 0; i < TN; ++i) gv[i] = gos[o * LD + lane + 32 * i];
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int i = 0; i < TN; ++i) acc[r][i] = fmaf(wv[r], gv[i], acc[r][i]);
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if (j0 + r < Cin) {
-#pragma unroll
-            for (int i = 0; i < TN; ++i)
-              if (lane + 32 * i < npos_pad) gxas[(j0 + r) * LD + lane + 32 * i] = acc[r][i];
+              for (int i = 0; i < TN; ++i) acc[r][i] = fmaf(wv[r], gv[i], acc[r][i]);
           }
         }
-      }
-      // bias row: gxa[Cin][pos] = sum_o bf[o] gout[o][pos]
-      for (int pos = tid; pos < npos_pad; pos += 256) {
-        float s = 0.f;
-        for (int o = 0; o < Cout; ++o) s = fmaf(bfs[b * Cout + o], gos[o * LD + pos], s);
-        gxas[Cin * LD + pos] = s;
+        if (ks == 1) {
+          if (act) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (j0 + r < Cin) {
+#pragma unroll
+                for (int i = 0; i < TN; ++i)
+                  if (lane + 32 * i < npos_pad) gxas[(j0 + r) * LD + lane + 32 * i] = acc[r][i];
+              }
+          }
+          // bias row: gxa[Cin][pos] = sum_o bf[o] gout[o][pos]
+          for (int pos = tid - 256; pos < npos_pad; pos += 256) {
+            float sres = 0.f;
+            for (int o = 0; o < Cout; ++o) sres = fmaf(bfs[b * Cout + o], gos[o * LD + pos], sres);
+            gxas[Cin * LD + pos] = sres;
+          }
+        }
+        __syncthreads();
+        if (ks == 0 && act) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (j0 + r < Cin) {
+#pragma unroll
+              for (int i = 0; i < TN; ++i)
+                if (lane + 32 * i < npos_pad) gxas[(j0 + r) * LD + lane + 32 * i] += acc[r][i];
+            }
+        }
       }
 
-      // ================= (b) xa_b recompute    (warp = (frame, w half), lane = channel pair)
-      for (int it = warp; it < 2 * pv; it += 8) {
-        const int l = it >> 1, half = it & 1;
+      // ================= (b) xa_b recompute    (warp = (frame, w half, channel half), lane = channel)
+      for (int it = warp; it < 4 * pv; it += AMB_NT / 32) {
+        const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
         const float* xm_l = xms + ((b * PCH + l) * K) * KP2 + half * WH;
         for (int cg = 0; cg < Cin; cg += 64) {
-          const int c0 = cg + lane, c1 = c0 + 32;
-          const bool v0ok = c0 < Cin, v1ok = c1 < Cin;
-          float x0[KP], x1[KP];
+          const int c0 = cg + chalf * 32 + lane;
+          const bool v0ok = c0 < Cin;
+          float x0[KP];
 #pragma unroll
           for (int i = 0; i < KP / 4; ++i) {
             const float4 t0 = *reinterpret_cast<const float4*>(xs + (v0ok ? c0 : 0) * LD + l * KP + 4 * i);
-            const float4 t1 = *reinterpret_cast<const float4*>(xs + (v1ok ? c1 : 0) * LD + l * KP + 4 * i);
             x0[4 * i] = t0.x; x0[4 * i + 1] = t0.y; x0[4 * i + 2] = t0.z; x0[4 * i + 3] = t0.w;
-            x1[4 * i] = t1.x; x1[4 * i + 1] = t1.y; x1[4 * i + 2] = t1.z; x1[4 * i + 3] = t1.w;
           }
-          float a0[WH], a1[WH];
+          float a0[WH];
 #pragma unroll
-          for (int j = 0; j < WH; ++j) a0[j] = a1[j] = 0.f;
+          for (int j = 0; j < WH; ++j) a0[j] = 0.f;
 #pragma unroll
           for (int v = 0; v < KP; ++v) {
             if (v < K) {
@@ -195,33 +214,24 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
                 a0[j4 * 4 + 1] = fmaf(x0[v], m.y, a0[j4 * 4 + 1]);
                 a0[j4 * 4 + 2] = fmaf(x0[v], m.z, a0[j4 * 4 + 2]);
                 a0[j4 * 4 + 3] = fmaf(x0[v], m.w, a0[j4 * 4 + 3]);
-                a1[j4 * 4 + 0] = fmaf(x1[v], m.x, a1[j4 * 4 + 0]);
-                a1[j4 * 4 + 1] = fmaf(x1[v], m.y, a1[j4 * 4 + 1]);
-                a1[j4 * 4 + 2] = fmaf(x1[v], m.z, a1[j4 * 4 + 2]);
-                a1[j4 * 4 + 3] = fmaf(x1[v], m.w, a1[j4 * 4 + 3]);
               }
             }
           }
 #pragma unroll
           for (int j4 = 0; j4 < WH / 4; ++j4) {
-            if (half * WH + 4 * j4 < KP) {
-              if (v0ok)
-                *reinterpret_cast<float4*>(xas + c0 * LD + l * KP + half * WH + 4 * j4) =
-                    make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
-              if (v1ok)
-                *reinterpret_cast<float4*>(xas + c1 * LD + l * KP + half * WH + 4 * j4) =
-                    make_float4(a1[4 * j4], a1[4 * j4 + 1], a1[4 * j4 + 2], a1[4 * j4 + 3]);
-            }
+            if (half * WH + 4 * j4 < KP && v0ok)
+              *reinterpret_cast<float4*>(xas + c0 * LD + l * KP + half * WH + 4 * j4) =
+                  make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
           }
         }
-        if (lane < WH && half * WH + lane < KP) {   // ones row: column sums of xmu (zero on padded columns)
-          float s = 0.f;
-          for (int v = 0; v < K; ++v) s += xm_l[v * KP2 + lane];
-          xas[Cin * LD + l * KP + half * WH + lane] = s;
+        if (chalf == 0 && lane < WH && half * WH + lane < KP) {   // ones row: column sums of xmu (0 on padded columns)
+          float sres = 0.f;
+          for (int v = 0; v < K; ++v) sres += xm_l[v * KP2 + lane];
+          xas[Cin * LD + l * KP + half * WH + lane] = sres;
         }
       }
       // frames beyond pv: xa must read as zero in (c)
-      for (int i = tid; i < C1 * (PCH - pv) * KP; i += 256) {
+      for (int i = tid; i < C1 * (PCH - pv) * KP; i += AMB_NT) {
         int c = i / ((PCH - pv) * KP), j = i - c * ((PCH - pv) * KP);
         xas[c * LD + pv * KP + j] = 0.f;
       }
@@ -231,7 +241,9 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
       if (o0 < Cout) {
         const int j0c = min(lane, Cin - 1), j1c = min(lane + 32, Cin - 1);
         const int nr = min(8, Cout - o0);
-        for (int p4 = 0; p4 < npos_pad; p4 += 4) {
+        const int phalf = ((npos_pad / 4 + 1) / 2) * 4;          // the two warp groups split the positions
+        const int pb = (warp >> 3) * phalf, pe = (warp >> 3) ? npos_pad : phalf;
+        for (int p4 = pb; p4 < pe; p4 += 4) {
           const float4 b0 = *reinterpret_cast<const float4*>(xas + j0c * LD + p4);
           const float4 b1 = *reinterpret_cast<const float4*>(xas + j1c * LD + p4);
 #pragma unroll
@@ -260,24 +272,22 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
         accb[b] += s;
       }
 
-      // ================= (d) gx += gxa_b xmu_b^T    (warp = (frame, v half), lane = channel pair)
-      for (int it = warp; it < 2 * pv; it += 8) {
-        const int l = it >> 1, half = it & 1;
+      // ================= (d) gx += gxa_b xmu_b^T    (warp = (frame, v half, channel half), lane = channel)
+      for (int it = warp; it < 4 * pv; it += AMB_NT / 32) {
+        const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
         const float* xmT_l = xmT + ((b * PCH + l) * K) * KP2 + half * WH;
         for (int cg = 0; cg < Cin; cg += 64) {
-          const int c0 = cg + lane, c1 = c0 + 32;
-          const bool v0ok = c0 < Cin, v1ok = c1 < Cin;
-          float g0[KP], g1[KP];
+          const int c0 = cg + chalf * 32 + lane;
+          const bool v0ok = c0 < Cin;
+          float g0[KP];
 #pragma unroll
           for (int i = 0; i < KP / 4; ++i) {
             const float4 t0 = *reinterpret_cast<const float4*>(gxas + (v0ok ? c0 : 0) * LD + l * KP + 4 * i);
-            const float4 t1 = *reinterpret_cast<const float4*>(gxas + (v1ok ? c1 : 0) * LD + l * KP + 4 * i);
             g0[4 * i] = t0.x; g0[4 * i + 1] = t0.y; g0[4 * i + 2] = t0.z; g0[4 * i + 3] = t0.w;
-            g1[4 * i] = t1.x; g1[4 * i + 1] = t1.y; g1[4 * i + 2] = t1.z; g1[4 * i + 3] = t1.w;
           }
-          float a0[WH], a1[WH];
+          float a0[WH];
 #pragma unroll
-          for (int j = 0; j < WH; ++j) a0[j] = a1[j] = 0.f;
+          for (int j = 0; j < WH; ++j) a0[j] = 0.f;
 #pragma unroll
           for (int w = 0; w < KP; ++w) {
             if (w < K) {
@@ -289,28 +299,16 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
                 a0[j4 * 4 + 1] = fmaf(g0[w], m.y, a0[j4 * 4 + 1]);
                 a0[j4 * 4 + 2] = fmaf(g0[w], m.z, a0[j4 * 4 + 2]);
                 a0[j4 * 4 + 3] = fmaf(g0[w], m.w, a0[j4 * 4 + 3]);
-                a1[j4 * 4 + 0] = fmaf(g1[w], m.x, a1[j4 * 4 + 0]);
-                a1[j4 * 4 + 1] = fmaf(g1[w], m.y, a1[j4 * 4 + 1]);
-                a1[j4 * 4 + 2] = fmaf(g1[w], m.z, a1[j4 * 4 + 2]);
-                a1[j4 * 4 + 3] = fmaf(g1[w], m.w, a1[j4 * 4 + 3]);
               }
             }
           }
 #pragma unroll
           for (int j4 = 0; j4 < WH / 4; ++j4) {
-            if (half * WH + 4 * j4 < KP) {
-              if (v0ok) {
-                float4* d = reinterpret_cast<float4*>(gxs + c0 * LD + l * KP + half * WH + 4 * j4);
-                float4 t = make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
-                if (b > 0) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-                *d = t;
-              }
-              if (v1ok) {
-                float4* d = reinterpret_cast<float4*>(gxs + c1 * LD + l * KP + half * WH + 4 * j4);
-                float4 t = make_float4(a1[4 * j4], a1[4 * j4 + 1], a1[4 * j4 + 2], a1[4 * j4 + 3]);
-                if (b > 0) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-                *d = t;
-              }
+            if (half * WH + 4 * j4 < KP && v0ok) {
+              float4* d = reinterpret_cast<float4*>(gxs + c0 * LD + l * KP + half * WH + 4 * j4);
+              float4 t = make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
+              if (b > 0) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+              *d = t;
             }
           }
         }
@@ -320,7 +318,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
       {
         constexpr int NT4 = KP / 4;
         const int ntile = pv * NT4 * NT4;
-        for (int tile = tid; tile < ntile; tile += 256) {
+        for (int tile = tid; tile < ntile; tile += AMB_NT) {
           const int wt = tile % NT4;
           int t = tile / NT4;
           const int vt = t % NT4, l = t / NT4;
@@ -362,7 +360,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
     {
       const int npos = pv * K;
       float* gb = q.gx.p + (long long)n * q.gx.sn + (long long)p0 * q.gx.sp;
-      for (int i = tid; i < Cin * npos; i += 256) {
+      for (int i = tid; i < Cin * npos; i += AMB_NT) {
         int c = i / npos, j = i - c * npos;
         int l = j / K, k = j - l * K;
         gb[(long long)c * q.gx.sc + (long long)l * q.gx.sp + (long long)k * q.gx.sk] = gxs[c * LD + l * KP + k];
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_bwd_kernel(AggMixBwdParams q) {
   }
 
   // ---- per-CTA partials of the conv_f gradients
-  float* pw = q.part_w + (long long)blockIdx.x * nb * Cout * Cin;
+  float* pw = q.part_w + ((long long)blockIdx.x * 2 + (warp >> 3)) * nb * Cout * Cin;
   float* pb = q.part_b + (long long)blockIdx.x * nb * Cout;
 #pragma unroll
   for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
@@ -429,6 +427,7 @@ int aggmix_bwd_ctas(int N, int P, int K, int Cin, int Cout, int nb) {
   long long items = (long long)N * ((P + g.PCH - 1) / g.PCH);
   return (int)(items < 148 ? items : 148);
 }
+// per-CTA weight-gradient partials: two (one per warp group)
 
 int launch_aggmix_bwd(AggMixBwdParams q, cudaStream_t st) {
   AggMixBwdGeom g;
@@ -440,7 +439,7 @@ int launch_aggmix_bwd(AggMixBwdParams q, cudaStream_t st) {
   if (g.KP == KP_ && g.TN == TN_) {                                  \
     auto kern = aggmix_bwd_kernel<KP_, TN_>;                         \
     ensure_max_smem((const void*)kern);                              \
-    kern<<<ctas, 256, g.smem, st>>>(q);                              \
+    kern<<<ctas, AMB_NT, g.smem, st>>>(q);                              \
   }
   DSTD_AMB(24, 3) DSTD_AMB(24, 4) DSTD_AMB(28, 3) DSTD_AMB(28, 4)
   DSTD_AMB(36, 3) DSTD_AMB(36, 4) DSTD_AMB(40, 3) DSTD_AMB(40, 4)

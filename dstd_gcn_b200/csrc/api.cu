@@ -56,7 +56,7 @@ static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
                      G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, (size_t)(S1 > 296 ? S1 : 296) * 4 * nb * C1 * 4,
                      (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4,
-                     (size_t)148 * nb * Cout * Cin * 4, (size_t)148 * nb * Cout * 4});
+                     (size_t)296 * nb * Cout * Cin * 4, (size_t)148 * nb * Cout * 4});
 }
 
 static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const dstd_branch* br, const char* fn) {
@@ -220,7 +220,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   float* p_wrm = ar.take<float>((size_t)S2 * nb * P * (2 * P + 1));
   float* p_adj = ar.take<float>((size_t)S2 * nb * K * K);
   float* p_alpha = ar.take<float>((size_t)S2 * nb);
-  float* p_wf = ar.take<float>((size_t)148 * nb * Cout * Cin);
+  float* p_wf = ar.take<float>((size_t)296 * nb * Cout * Cin);
   float* p_bf = ar.take<float>((size_t)148 * nb * Cout);
 
   PackParams pk;
@@ -324,7 +324,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   for (int b = 0; b < nb; ++b) {
     const dstd_branch_grad& g = a->gbr[b];
     if (fused) {
-      seg(p_wf + (long long)b * Cout * Cin, n_wf, (long long)nb * Cout * Cin, Cout, Cin, Cin, g.w_f, Cin);
+      seg(p_wf + (long long)b * Cout * Cin, 2 * n_wf, (long long)nb * Cout * Cin, Cout, Cin, Cin, g.w_f, Cin);
       seg(p_bf + (long long)b * Cout, n_wf, (long long)nb * Cout, Cout, 1, 1, g.b_f, 1);
     } else {
       seg(p_wcat + b * C1, S1a, st_wcat, Cout, Cin, nb * C1, g.w_f, Cin);
