@@ -126,7 +126,7 @@ static BwdGeom bwd_geom(int P, int K) {
   g.ECP = ec <= 36 ? 36 : ec <= 68 ? 68 : ec <= 100 ? 100 : ((ec + 31) / 32 * 32 + 4);
   g.WLD = ((2 * P + 7) / 8) * 8;
   size_t pk4 = (size_t)((4 * P * K + 3) & ~3);
-  g.smem_floats = 2 * pk4 + (size_t)P * g.ECP + (size_t)(2 * P + 1) * g.ECP + (size_t)P * g.WLD +
+  g.smem_floats = 2 * pk4 + (size_t)2 * P * g.ECP + (size_t)(2 * P + 1) * g.ECP + (size_t)P * g.WLD +
                   (size_t)((K * K + 3) & ~3) + 32;
   return g;
 }
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
   const int pk4 = (4 * PK + 3) & ~3;
   float* ms = smem;                    // [4][PK]
   float* gms = ms + pk4;               // [4][PK]
-  float* gX = gms + pk4;               // [P][ECP]
-  float* Ds = gX + P * ECP;            // [2P+1][ECP]
+  float* gX = gms + pk4;               // [2][P][ECP]  double buffered (cp.async prefetch of the next chunk)
+  float* Ds = gX + 2 * P * ECP;        // [2P+1][ECP]
   float* Ws = Ds + (P2 + 1) * ECP;     // [P][WLD]
   float* gA = Ws + P * WLD;            // [KK]
   float* red = gA + ((KK + 3) & ~3);   // [32]
@@ -178,124 +178,157 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
 
   const int n_kt = (P2 + 7) / 8, n_et = ECP / 4;
 
-  for (int n = blockIdx.x; n < q.N; n += gridDim.x) {
+  // per-lane decode of the <= 4 chunk columns it touches (ec = lane + 32 i -> local row vl, column w)
+  int c_vl[4], c_w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ec = lane + 32 * i;
+    c_vl[i] = ec / K;
+    c_w[i] = ec - c_vl[i] * K;
+  }
+  const int nchunks = (K + RV - 1) / RV;
+  const int nsamp = (q.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long total = (long long)nsamp * nchunks;     // (sample, chunk) steps of this CTA
+
+  // cp.async prefetch of the gxm chunk of step `st` into buffer st & 1 (zero filled beyond the chunk)
+  auto prefetch = [&](long long st) {
+    const int n = (int)blockIdx.x + (int)(st / nchunks) * (int)gridDim.x;
+    const int v0 = (int)(st % nchunks) * RV;
+    const int EC = min(RV, K - v0) * K, e0 = v0 * K;
+    const float* src = q.gxm + ((long long)n * q.nb + b) * P * KK + e0;
+    float* dst = gX + (st & 1) * P * ECP;
+    for (int p = ty; p < P; p += 8)
+      for (int ec = lane; ec < ECP; ec += 32) cp_async4(dst + p * ECP + ec, src + (long long)p * KK + ec, ec < EC);
+  };
+  if (total > 0) prefetch(0);
+
+  for (long long st = 0; st < total; ++st) {
+    const int n = (int)blockIdx.x + (int)(st / nchunks) * (int)gridDim.x;
+    const int ci = (int)(st % nchunks);
+    const int v0 = ci * RV, rows = min(RV, K - v0), EC = rows * K, e0 = v0 * K;
     const long long nb_ = (long long)n * q.nb + b;
-    const float* mg = q.m + nb_ * 4 * PK;
-    const float* gxm = q.gxm + nb_ * P * KK;
-    const float* pdg = q.pd + nb_ * P * KK;
-    __syncthreads();
-    for (int i = tid; i < 4 * PK; i += 256) {
-      ms[i] = __ldg(mg + i);
-      gms[i] = 0.f;
+    const float* gXc = gX + (st & 1) * P * ECP;
+    if (ci == 0) {   // new sample: its reduction rows, zeroed gradient rows
+      __syncthreads();
+      const float* mg = q.m + nb_ * 4 * PK;
+      for (int i = tid; i < 4 * PK; i += 256) {
+        ms[i] = __ldg(mg + i);
+        gms[i] = 0.f;
+      }
     }
-    for (int v0 = 0; v0 < K; v0 += RV) {
-      const int rows = min(RV, K - v0), EC = rows * K, e0 = v0 * K;
-      __syncthreads();
-      // 1. stage gXm chunk (zero padded) ; galpha += gxm * pd
-      for (int i = tid; i < P * ECP; i += 256) {
-        int p = i / ECP, ec = i - p * ECP;
-        float g = 0.f;
-        if (ec < EC) {
-          long long o = (long long)p * KK + e0 + ec;
-          g = __ldg(gxm + o);
-          galpha = fmaf(g, __ldg(pdg + o), galpha);
-        }
-        gX[i] = g;
-      }
-      // 2. rebuild D chunk (+ ones row for the bias gradient)
-      for (int i = tid; i < (P2 + 1) * ECP; i += 256) {
-        int k = i / ECP, ec = i - k * ECP;
-        float d = 0.f;
-        if (ec < EC) {
-          if (k < P2) {
-            int r = (k >= P) ? 1 : 0, qq = k - r * P;
-            int vl = ec / K, w = ec - vl * K;
-            d = fast_tanh(ms[r * PK + qq * K + v0 + vl] - ms[(2 + r) * PK + qq * K + w]);
-          } else {
-            d = 1.0f;
+    cp_async_wait_all();
+    __syncthreads();                       // chunk st landed; everyone is done with the other buffer and with Ds
+    if (st + 1 < total) prefetch(st + 1);  // overlaps with the whole chunk below
+
+    // 2. rebuild D chunk (+ ones row for the bias gradient); galpha += gxm * pd on the way
+    {
+      const float* pdg = q.pd + nb_ * P * KK + e0;
+      for (int k = ty; k <= P2; k += 8) {
+        const int r = (k >= P) ? 1 : 0, qq = k - r * P;
+        const float* m1 = ms + r * PK + qq * K + v0;
+        const float* m2 = ms + (2 + r) * PK + qq * K;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ec = lane + 32 * i;
+          if (ec < ECP) {
+            float d = 0.f;
+            if (ec < EC) d = (k < P2) ? fast_tanh(m1[c_vl[i]] - m2[c_w[i]]) : 1.0f;
+            Ds[k * ECP + ec] = d;
           }
         }
-        Ds[i] = d;
       }
-      __syncthreads();
-      // 3a. static-adjacency gradient: sum over p
-      if (tid < EC) {
-        float s = 0.f;
-        for (int p = 0; p < P; ++p) s += gX[p * ECP + tid];
-        gA[e0 + tid] += s;
+      for (int p = ty; p < P; p += 8) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ec = lane + 32 * i;
+          if (ec < EC) galpha = fmaf(gXc[p * ECP + ec], __ldg(pdg + (long long)p * KK + ec), galpha);
+        }
       }
-      // 3b. gWrm (+bias column) += gXm * D^T
-      for (int e4 = 0; e4 < ECP; e4 += 4) {
-        float4 g4[TMA], d4[TNA];
+    }
+    __syncthreads();
+    // 3a. static-adjacency gradient: sum over p
+    if (tid < EC) {
+      float s = 0.f;
+      for (int p = 0; p < P; ++p) s += gXc[p * ECP + tid];
+      gA[e0 + tid] += s;
+    }
+    // 3b. gWrm (+bias column) += gXm * D^T
+    for (int e4 = 0; e4 < ECP; e4 += 4) {
+      float4 g4[TMA], d4[TNA];
 #pragma unroll
-        for (int a = 0; a < TMA; ++a) g4[a] = *reinterpret_cast<const float4*>(gX + prow[a] * ECP + e4);
+      for (int a = 0; a < TMA; ++a) g4[a] = *reinterpret_cast<const float4*>(gXc + prow[a] * ECP + e4);
 #pragma unroll
-        for (int c = 0; c < TNA; ++c) d4[c] = *reinterpret_cast<const float4*>(Ds + kcol[c] * ECP + e4);
+      for (int c = 0; c < TNA; ++c) d4[c] = *reinterpret_cast<const float4*>(Ds + kcol[c] * ECP + e4);
 #pragma unroll
-        for (int a = 0; a < TMA; ++a)
+      for (int a = 0; a < TMA; ++a)
 #pragma unroll
-          for (int c = 0; c < TNA; ++c) {
-            accW[a][c] = fmaf(g4[a].x, d4[c].x, accW[a][c]);
-            accW[a][c] = fmaf(g4[a].y, d4[c].y, accW[a][c]);
-            accW[a][c] = fmaf(g4[a].z, d4[c].z, accW[a][c]);
-            accW[a][c] = fmaf(g4[a].w, d4[c].w, accW[a][c]);
-          }
-      }
-      __syncthreads();
-      // 4. gS = alpha * (Wrm^T gXm) * (1 - D^2), written over D
-      for (int tile = tid; tile < n_kt * n_et; tile += 256) {
-        int kt = tile / n_et, et = tile - kt * n_et;
-        float acc[8][4];
+        for (int c = 0; c < TNA; ++c) {
+          accW[a][c] = fmaf(g4[a].x, d4[c].x, accW[a][c]);
+          accW[a][c] = fmaf(g4[a].y, d4[c].y, accW[a][c]);
+          accW[a][c] = fmaf(g4[a].z, d4[c].z, accW[a][c]);
+          accW[a][c] = fmaf(g4[a].w, d4[c].w, accW[a][c]);
+        }
+    }
+    __syncthreads();
+    // 4. gS = alpha * (Wrm^T gXm) * (1 - D^2), written over D
+    for (int tile = tid; tile < n_kt * n_et; tile += 256) {
+      const int kt = tile / n_et, et = tile - kt * n_et;
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      const float* wp = Ws + kt * 8;
+      const float* gp = gXc + et * 4;
+#pragma unroll 5
+      for (int p = 0; p < P; ++p) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + p * WLD);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + p * WLD + 4);
+        const float4 g = *reinterpret_cast<const float4*>(gp + p * ECP);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        for (int p = 0; p < P; ++p) {
-          float4 w0 = *reinterpret_cast<const float4*>(Ws + p * WLD + kt * 8);
-          float4 w1 = *reinterpret_cast<const float4*>(Ws + p * WLD + kt * 8 + 4);
-          float4 g = *reinterpret_cast<const float4*>(gX + p * ECP + et * 4);
-          float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-          float gv[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], gv[j], acc[i][j]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int k = kt * 8 + i;
-          if (k < P2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              int ec = et * 4 + j;
-              float d = Ds[k * ECP + ec];
-              Ds[k * ECP + ec] = alpha * acc[i][j] * (1.0f - d * d);
-            }
-          }
-        }
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], gv[j], acc[i][j]);
       }
-      __syncthreads();
-      // 5. gm1[k,v] = sum_w gS ; gm2[k,w] = -sum_v gS
-      for (int i = tid; i < P2 * rows; i += 256) {
-        int k = i / rows, vl = i - k * rows;
-        const float* row = Ds + k * ECP + vl * K;
-        float s = 0.f;
-        for (int w = 0; w < K; ++w) s += row[w];
-        int r = (k >= P) ? 1 : 0, qq = k - r * P;
-        gms[r * PK + qq * K + v0 + vl] += s;
-      }
-      for (int i = tid; i < P2 * K; i += 256) {
-        int k = i / K, w = i - k * K;
-        const float* col = Ds + k * ECP + w;
-        float s = 0.f;
-        for (int vl = 0; vl < rows; ++vl) s += col[vl * K];
-        int r = (k >= P) ? 1 : 0, qq = k - r * P;
-        gms[(2 + r) * PK + qq * K + w] -= s;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kt * 8 + i;
+        if (k < P2) {
+          float4* dp = reinterpret_cast<float4*>(Ds + k * ECP + et * 4);
+          float4 d = *dp;
+          d.x = alpha * acc[i][0] * (1.0f - d.x * d.x);
+          d.y = alpha * acc[i][1] * (1.0f - d.y * d.y);
+          d.z = alpha * acc[i][2] * (1.0f - d.z * d.z);
+          d.w = alpha * acc[i][3] * (1.0f - d.w * d.w);
+          *dp = d;
+        }
       }
     }
     __syncthreads();
-    float* gmg = q.gm + nb_ * 4 * PK;
-    for (int i = tid; i < 4 * PK; i += 256) gmg[i] = gms[i];
+    // 5. gm1[k,v] = sum_w gS (lanes 24.. : one local row each) ; gm2[k,w] = -sum_v gS (lanes 0..K-1, K <= 24;
+    //    wider K: second pass)
+    for (int k = ty; k < P2; k += 8) {
+      const int r = (k >= P) ? 1 : 0, qq = k - r * P;
+      const float* drow = Ds + k * ECP;
+      for (int w = lane; w < K; w += 32) {
+        float s = 0.f;
+        for (int vl = 0; vl < rows; ++vl) s += drow[vl * K + w];
+        gms[(2 + r) * PK + qq * K + w] -= s;
+      }
+      const int vl = 31 - lane;              // the last lanes take the row sums
+      if (vl < rows) {
+        float s = 0.f;
+        for (int w = 0; w < K; ++w) s += drow[vl * K + w];
+        gms[r * PK + qq * K + v0 + vl] += s;
+      }
+    }
+    if (ci == nchunks - 1) {                 // sample finished: its gm rows go out
+      __syncthreads();
+      float* gmg = q.gm + nb_ * 4 * PK;
+      for (int i = tid; i < 4 * PK; i += 256) gmg[i] = gms[i];
+    }
   }
 
   // per-split partials
