@@ -195,6 +195,88 @@ def workload_config(args, batch_override=None):
                                           "inputs rotate over 4 distinct batches"}
 
 
+# =============================================================================================== inference sweep
+def run_infer(args, model, be, dev, rank, world, t, v, t_in):
+    """Eval-mode forward throughput (engine/prediction.py:340-353): BatchNorm on running statistics, no_grad, the whole
+    forward captured in one CUDA graph; replicas only (no collective)."""
+    import torch
+    import torch.distributed as dist
+    host = [synthetic_batch(args.batch, t, v, t_in, seed=777 + rank * 1000 + i)[0].view(args.batch, t, v, 3).pin_memory()
+            for i in range(4)]
+    with torch.no_grad():
+        model.train()
+        for i in range(2):                       # move the running statistics off (0, 1) as two training steps would
+            model(host[i].to(dev))
+        model.eval()
+        static_in = host[0].to(dev)
+        resident = [h.to(dev) for h in host]
+        for _ in range(2):
+            out = model(static_in)
+        torch.cuda.synchronize()
+        l0 = be.launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = model(static_in)
+        launches_per_step = be.launches - l0
+    out_host = torch.empty_like(static_out, device="cpu").pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(e2e, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            static_in.copy_(host[i % 4] if e2e else resident[i % 4], non_blocking=True)
+            graph.replay()
+            if e2e:
+                out_host.copy_(static_out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    timed(False, args.warmup)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(False, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(True, args.steps)
+    if rank == 0:
+        total = args.batch * world * args.steps
+        sps, sps_e2e = total / (ms * 1e-3), total / (ms_e2e * 1e-3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        chans = [(6, C_FEAT)] + [(C_FEAT, C_FEAT)] * N_LAYERS + [(C_FEAT, 3)]
+        bytes_fwd = 4 * t * v * sum(ci + co for ci, co in chans)
+        achieved = sps / world * bytes_fwd / 1e9
+        cfg = workload_config(args)
+        cfg["workload"] = cfg["workload"].replace("training step with inverse pass", "eval-mode forward (BN on running stats)")
+        cfg["variant"] = args.variant
+        print(json.dumps({
+            "metric": "infer_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": host[0].numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "cuda_graph": True, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "scope": f"forward only: {bytes_fwd} algorithmic B per sample (SURVEY.md 8d)"},
+        }), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 # =============================================================================================== GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -204,6 +286,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
     ap.add_argument("--workload", default="h36m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: the headline metric; infer: eval-mode forward sweep (BASELINE.json config 4)")
+    ap.add_argument("--variant", default="dstdgcn", choices=["dstdgcn", "dstdgcn_fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
@@ -219,6 +304,8 @@ def main():
     from dstd_gcn_b200 import _lib
     from dstd_gcn_b200.engine import TrainStep
     from dstd_gcn_b200.model import dstdgcn as std
+    if args.variant == "dstdgcn_fast":
+        from dstd_gcn_b200.model import dstdgcn_fast as std
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -233,8 +320,11 @@ def main():
     t = t_in + t_out
     torch.manual_seed(777)                       # identical replicas on every rank
     model = perturb(std.DSTDGCN(6, t_in, t_out, drop, v, C_FEAT, N_LAYERS, layout)).to(dev).train()
-    step = TrainStep(model, lr=3e-3, inverse=True)
     be = _lib.backend()
+    if args.mode == "infer":
+        run_infer(args, model, be, dev, rank, world, t, v, t_in)
+        return
+    step = TrainStep(model, lr=3e-3, inverse=True)
 
     nbuf = 4
     host = [synthetic_batch(args.batch, t, v, t_in, seed=777 + rank * 1000 + i) for i in range(nbuf)]

@@ -141,14 +141,13 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm, fused ? wcatT : nullptr);
   if ((rc = launch_pack(pk, st))) return rc;
 
-  // 1. m = [conv_m1; conv_m2] x + b        (all branches in one pass over x)
-  BgemmParams g1;
-  g1.M = 4 * nb; g1.Kd = C1; g1.G = G; g1.P = P; g1.K = K;
-  g1.w = wm; g1.wsc = 1; g1.wsi = C1; g1.bias = nullptr;
-  g1.in = mk(a->x); g1.ones_row = Cin;
-  g1.out = dense_view(a->m, 4 * nb, P, K);
-  g1.add = View4{nullptr, 0, 0, 0, 0};
-  if ((rc = launch_bgemm(g1, st))) return rc;
+  // 1. m = [conv_m1; conv_m2] x + b        (all branches in one streaming pass over x)
+  {
+    MprojFwdParams mp;
+    mp.Cin = Cin; mp.J = 4 * nb; mp.P = P; mp.K = K; mp.G = G;
+    mp.x = mk(a->x); mp.wm = wm; mp.m = a->m;
+    if ((rc = launch_mproj_fwd(mp, st))) return rc;
+  }
 
   // 2. pd = conv_rm(tanh(m1 - m2))         (pairwise tensor stays on chip)
   DynAdjFwdParams dp;

@@ -400,3 +400,58 @@ int launch_mproj_bwd(const MprojBwdParams& q, cudaStream_t st) {
 }
 
 }  // namespace dstd
+
+// ================================================================================= mproj forward
+// m[n,j,p,k] = sum_c wm[j][c] x[n,c,p,k] + wm[j][Cin]   for the J = 4*nb reduction rows (conv_m1 / conv_m2 of every
+// branch, model/dstdgcn.py:82) in one streaming pass over x: thread = column, 8 channels in flight, weights broadcast
+// from shared memory.  HBM bound: reads the tile once, writes J/C of a tile.
+namespace dstd {
+
+__global__ void __launch_bounds__(256) mproj_fwd_kernel(MprojFwdParams q) {
+  extern __shared__ __align__(16) float wmT[];   // [Cin+1][8]
+  const int Cin = q.Cin, C1 = Cin + 1, J = q.J, PK = q.P * q.K;
+  for (int i = threadIdx.x; i < C1 * 8; i += 256) {
+    const int c = i >> 3, j = i & 7;
+    wmT[i] = j < J ? __ldg(q.wm + (long long)j * C1 + c) : 0.f;
+  }
+  __syncthreads();
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= q.G) return;
+  const int n = (int)(g / PK);
+  const int rem = (int)(g - (long long)n * PK);
+  const int p = rem / q.K, k = rem - p * q.K;
+  const float* xp = q.x.p + vix(q.x, n, 0, p, k);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = wmT[Cin * 8 + j];
+  for (int c0 = 0; c0 < Cin; c0 += 8) {
+    float xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xv[u] = (c0 + u < Cin) ? __ldg(xp + (long long)(c0 + u) * q.x.sc) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < Cin) {
+        const float4 wa = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8 + 4);
+        acc[0] = fmaf(wa.x, xv[u], acc[0]); acc[1] = fmaf(wa.y, xv[u], acc[1]);
+        acc[2] = fmaf(wa.z, xv[u], acc[2]); acc[3] = fmaf(wa.w, xv[u], acc[3]);
+        acc[4] = fmaf(wb.x, xv[u], acc[4]); acc[5] = fmaf(wb.y, xv[u], acc[5]);
+        acc[6] = fmaf(wb.z, xv[u], acc[6]); acc[7] = fmaf(wb.w, xv[u], acc[7]);
+      }
+    }
+  }
+  float* mp = q.m + (long long)n * J * PK + rem;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < J) mp[(long long)j * PK] = acc[j];
+}
+
+int launch_mproj_fwd(const MprojFwdParams& q, cudaStream_t st) {
+  DSTD_REQUIRE(q.J <= 8, DSTD_ERR_UNSUPPORTED, "mproj_fwd: J=%d > 8", q.J);
+  const size_t smem = (size_t)(q.Cin + 1) * 8 * sizeof(float);
+  mproj_fwd_kernel<<<cdiv(q.G, 256), 256, smem, st>>>(q);
+  count_launch();
+  return check_launch("mproj_fwd");
+}
+
+}  // namespace dstd

@@ -45,6 +45,14 @@ struct MprojBwdParams {
   const float* wm;     // [J][Cin+1]
   float* partial;      // [ctas][J][Cin+1]
 };
+struct MprojFwdParams {
+  int Cin, J, P, K;
+  long long G;
+  View4 x;             // [N,Cin,P,K]
+  const float* wm;     // [J][Cin+1]  (bias in column Cin)
+  float* m;            // dense [N,J,P,K]
+};
+int launch_mproj_fwd(const MprojFwdParams& q, cudaStream_t st);
 bool mproj_bwd_supported(int Cin, int J);
 int mproj_bwd_ctas(long long G);
 int launch_mproj_bwd(const MprojBwdParams& q, cudaStream_t st);

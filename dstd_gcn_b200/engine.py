@@ -183,3 +183,79 @@ def predict(model, inputs):
     """Eval-mode forward on raw ``[N, T, 3V]`` batches (engine/prediction.py:340-353)."""
     n, t, vc = inputs.shape
     return model(inputs.view(n, t, vc // 3, 3)).reshape(n, t, vc)
+
+
+# ====================================================================================== checkpoints (reference format)
+class ModelWrapper(torch.nn.Module):
+    """Key-prefix twin of the reference's ``ModelWrapper`` (engine/prediction.py:22-101): checkpoints written by
+    ``PredictionEngine.save`` (:170-182) hold ``ModelWrapper.state_dict()``, i.e. every key starts with ``model.``."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, x, inverse=False):
+        return self.model(x)
+
+
+def _adam_state_dict(step: "TrainStep"):
+    """The flat Adam buckets in ``torch.optim.Adam.state_dict()`` layout (parameter index = position in
+    ``model.parameters()``, as the reference's ``optim.Adam(self.model.parameters())`` numbers them)."""
+    params = list(step.model.parameters())
+    index = {id(p): i for i, p in enumerate(params)}
+    state = {}
+    nsteps = int(step.step_dev.item())
+    for name, p in step.flat.named:
+        off, n, shape = step.flat.slices[name]
+        if nsteps > 0:
+            state[index[id(p)]] = {"step": torch.tensor(float(nsteps)),
+                                   "exp_avg": step.exp_avg[off:off + n].view(shape).clone(),
+                                   "exp_avg_sq": step.exp_avg_sq[off:off + n].view(shape).clone()}
+    group = {"lr": step.lr, "betas": tuple(step.betas), "eps": step.eps, "weight_decay": step.weight_decay,
+             "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+             "fused": None, "decoupled_weight_decay": False, "params": list(range(len(params)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def save_checkpoint(path, step: "TrainStep", err=float("inf"), epoch=0, scheduler_state=None):
+    """Write ``last.pth``-compatible state (engine/prediction.py:170-182): same top-level keys, ``model.``-prefixed
+    weights, Adam state in torch's own layout, so the reference's ``PredictionEngine.recover`` can read it back."""
+    state = {"lr": step.lr, "err": err, "model": ModelWrapper(step.model).state_dict(),
+             "optimizer": _adam_state_dict(step), "scheduler": scheduler_state or {}, "epoch": epoch}
+    torch.save(state, path)
+    return state
+
+
+def load_checkpoint(path_or_state, model, step: Optional["TrainStep"] = None, model_only=False):
+    """Counterpart of ``PredictionEngine.recover`` (engine/prediction.py:159-168).  Accepts checkpoints written by the
+    reference (keys prefixed ``model.``) as well as bare model state_dicts; strict key / shape matching."""
+    state = path_or_state if isinstance(path_or_state, dict) else torch.load(path_or_state, map_location="cpu",
+                                                                             weights_only=False)
+    sd = state["model"] if "model" in state and isinstance(state["model"], dict) else state
+    if all(k.startswith("model.") for k in sd):
+        sd = {k[len("model."):]: v for k, v in sd.items()}
+    with torch.no_grad():
+        own = model.state_dict()
+        missing = set(own) - set(sd)
+        extra = set(sd) - set(own)
+        if missing or extra:
+            raise RuntimeError(f"checkpoint does not match the model: missing {sorted(missing)[:3]}, "
+                               f"unexpected {sorted(extra)[:3]}")
+        for k, v in own.items():            # in place: parameters may be views into the flat bucket
+            v.copy_(sd[k].to(v.dtype))
+    if step is not None and not model_only and "optimizer" in state and state["optimizer"].get("state"):
+        params = list(model.parameters())
+        index = {id(p): i for i, p in enumerate(params)}
+        ost = state["optimizer"]["state"]
+        nsteps = 0
+        for name, p in step.flat.named:
+            off, n, shape = step.flat.slices[name]
+            st = ost.get(index[id(p)])
+            if st is None:
+                continue
+            step.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            step.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            nsteps = max(nsteps, int(float(st["step"])))
+        step.step_dev.fill_(nsteps)
+        step.set_lr(state.get("lr", step.lr))
+    return state.get("epoch", 0), state.get("err", float("inf"))
