@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
   float* xms = xs + ((Cin * XS_LD + 3) & ~3);        // [nb][PCH][K][KP]
   float* aeff = xms + nb * PCH * K * KP;             // [nb][K*K]
   float* pdr = aeff + ((nb * KK + 3) & ~3);          // [nb][PCH][K*K]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(pdr + ((nb * PCH * KK + 3) & ~3));
+  // layer-skip chunk [Cout][XS_LD] (only when a skip is fused): staged with the lanes walking the SKIP tensor's own
+  // contiguous direction, because the skip is kept in the other memory order (it is the block input)
+  float* sks = pdr + ((nb * PCH * KK + 3) & ~3);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sks + (q.skip.p ? ((Cout * XS_LD + 3) & ~3) : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
@@ -146,6 +149,25 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
       for (int b = 0; b < nb; ++b) {
         const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
         for (int i = tid; i < pv * KK; i += 256) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+      }
+      if (q.skip.p) {
+        // lane order (k major, l minor) when the skip is contiguous along p, else the position order
+        const bool p_fast = q.skip.sp == 1 && q.skip.sk != 1;
+        int soff[TNS], sdst[TNS];
+#pragma unroll
+        for (int i = 0; i < TNS; ++i) {
+          const int j = lane + 32 * i;
+          int l, k;
+          if (p_fast) { k = j / pv; l = j - k * pv; } else { l = j / K; k = j - l * K; }
+          soff[i] = j < npos ? (int)(l * q.skip.sp + k * q.skip.sk) : -1;
+          sdst[i] = l * K + k;
+        }
+        const float* sb = q.skip.p + (long long)n * q.skip.sn + (long long)p0 * q.skip.sp;
+        for (int o = warp; o < Cout; o += 8) {
+#pragma unroll
+          for (int i = 0; i < TNS; ++i)
+            if (soff[i] >= 0) cp_async4(sks + o * XS_LD + sdst[i], sb + (long long)o * q.skip.sc + soff[i], true);
+        }
       }
       cp_async_wait_all();
       __syncthreads();
@@ -253,7 +275,6 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
       const int l = pos / K, k = pos - l * K;
       const bool pok = pos < npos;
       const long long off_o = (long long)n * q.out.sn + (long long)(p0 + l) * q.out.sp + (long long)k * q.out.sk;
-      const long long off_s = q.skip.p ? (long long)n * q.skip.sn + (long long)(p0 + l) * q.skip.sp + (long long)k * q.skip.sk : 0;
       for (int col0 = (warp >> 2) * 32; col0 < NP; col0 += 64) {
         uint32_t r[32];
         const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
             const int o = col0 + j;
             if (o < Cout) {
               float v = ok ? __uint_as_float(r[j]) : __int_as_float(0x7fc00000);   // a stalled pipeline must be loud
-              if (q.skip.p) v += __ldg(q.skip.p + off_s + (long long)o * q.skip.sc);
+              if (q.skip.p) v += sks[o * XS_LD + pos];
               q.out.p[off_o + (long long)o * q.out.sc] = v;
             }
           }
@@ -319,7 +340,7 @@ struct TcGeom {
   size_t smem, wtc_floats;
 };
 
-static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g) {
+static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g, bool with_skip = true) {
   if (K > 40 || K < 1 || Cin > 64 || Cout > 64) return false;
   g.WH = K <= 24 ? 12 : K <= 32 ? 16 : 20;
   g.KD = (Cin + 1 + 7) / 8 * 8;
@@ -331,7 +352,8 @@ static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g) {
     if (pch > P && pch > 1) continue;
     const int XS_LD = (pch * K) | 1;
     size_t f = (size_t)2 * ((pch * K + 7) / 8) * sbo_f + g.wtc_floats + (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * pch * K * KP +
-               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + 8;
+               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + 8 +
+               (with_skip ? (size_t)((Cout * XS_LD + 3) & ~3) : 0);
     // the M = 128 descriptors read 16 row groups from each A tile: keep that window inside the allocation
     const size_t a_window = (size_t)((pch * K + 7) / 8) * sbo_f + (size_t)16 * sbo_f + 64;
     if (f < a_window) f = a_window;
@@ -359,7 +381,8 @@ size_t aggmix_tc_ws_floats(int Cin, int Cout, int P, int K, int nb) {
 
 int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cudaStream_t st) {
   TcGeom g;
-  DSTD_REQUIRE(tc_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g), DSTD_ERR_UNSUPPORTED, "aggmix_fwd_tc: shape outside limits");
+  DSTD_REQUIRE(tc_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g, q.skip.p != nullptr), DSTD_ERR_UNSUPPORTED,
+               "aggmix_fwd_tc: shape outside limits");
   int* err_flag = reinterpret_cast<int*>(wtc_ws + g.wtc_floats);
   const int nw = (int)g.wtc_floats + 4;   // image + error flag
   pack_tc_zero_kernel<<<min(cdiv(nw, 256), 64), 256, 0, st>>>(wtc_ws, nw);
