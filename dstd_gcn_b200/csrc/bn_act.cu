@@ -216,44 +216,30 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q) {
     }
   }
   for (int n = n0; n < n1; n += BN_U) {
-    // operands kept in the output's own order are loaded first, so that their latency overlaps the staging round trip
-    float yv[NJ][BN_U], rv[NJ][BN_U], mv[NJ][BN_U];
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-#pragma unroll
-      for (int u = 0; u < BN_U; ++u) {
-        const bool ok = tt[i] >= 0 && n + u < n1;
-        yv[i][u] = (ok && !y_stage) ? __ldg(q.y.p + vix(q.y, n + u, c, tt[i], vv[i])) : 0.f;
-        rv[i][u] = (ok && q.r.p && !r_stage) ? __ldg(q.r.p + vix(q.r, n + u, c, tt[i], vv[i])) : 0.f;
-        mv[i][u] = (ok && q.mask) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + tt[i]) * V + vv[i]) : 1.f;
-      }
-    }
     if (y_stage || r_stage) {
       __syncthreads();
       if (y_stage) stage_planes<NJ, BN_U>(q.y, c, n, n1, T, V, shy, TV);
       if (r_stage) stage_planes<NJ, BN_U>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) {
-        if (tt[i] >= 0) {
-          const int e = tt[i] * V + vv[i];
-#pragma unroll
-          for (int u = 0; u < BN_U; ++u) {
-            if (y_stage) yv[i][u] = shy[u * TV + e];
-            if (r_stage) rv[i][u] = shr[u * TV + e];
-          }
-        }
-      }
     }
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       if (tt[i] >= 0) {
+        const int t = tt[i], v = vv[i], e = t * V + v;
+        float yv[BN_U], rv[BN_U], mv[BN_U];
+#pragma unroll
+        for (int u = 0; u < BN_U; ++u) {
+          const bool ok = n + u < n1;
+          yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
+          rv[u] = !q.r.p ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
+          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+        }
 #pragma unroll
         for (int u = 0; u < BN_U; ++u) {
           if (n + u < n1) {
-            const float pre = fmaf(yv[i][u] - sm[i], sc[i], sf[i]) + rv[i][u];
+            const float pre = fmaf(yv[u] - sm[i], sc[i], sf[i]) + rv[u];
             const float a = pre > 0.f ? pre : slope * pre;
-            q.out.p[vix(q.out, n + u, c, tt[i], vv[i])] = a * mv[i][u];
+            q.out.p[vix(q.out, n + u, c, t, v)] = a * mv[u];
           }
         }
       }
@@ -320,44 +306,30 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q)
     }
   }
   for (int n = n0; n < n1; n += BN_UB) {
-    float yv[NJ][BN_UB], rv[NJ][BN_UB], gv[NJ][BN_UB], mv[NJ][BN_UB];
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-#pragma unroll
-      for (int u = 0; u < BN_UB; ++u) {
-        const bool ok = tt[i] >= 0 && n + u < n1;
-        gv[i][u] = ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, tt[i], vv[i])) : 0.f;
-        yv[i][u] = (ok && !y_stage) ? __ldg(q.y.p + vix(q.y, n + u, c, tt[i], vv[i])) : 0.f;
-        rv[i][u] = (ok && use_r && !r_stage) ? __ldg(q.r.p + vix(q.r, n + u, c, tt[i], vv[i])) : 0.f;
-        mv[i][u] = (ok && q.mask) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + tt[i]) * V + vv[i]) : 1.f;
-      }
-    }
     if (y_stage || r_stage) {
       __syncthreads();
       if (y_stage) stage_planes<NJ, BN_UB>(q.y, c, n, n1, T, V, shy, TV);
       if (r_stage) stage_planes<NJ, BN_UB>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) {
-        if (tt[i] >= 0) {
-          const int e = tt[i] * V + vv[i];
-#pragma unroll
-          for (int u = 0; u < BN_UB; ++u) {
-            if (y_stage) yv[i][u] = shy[u * TV + e];
-            if (r_stage) rv[i][u] = shr[u * TV + e];
-          }
-        }
-      }
     }
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       if (tt[i] >= 0) {
+        const int t = tt[i], v = vv[i], e = t * V + v;
+        float yv[BN_UB], rv[BN_UB], gv[BN_UB], mv[BN_UB];
+#pragma unroll
+        for (int u = 0; u < BN_UB; ++u) {
+          const bool ok = n + u < n1;
+          yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
+          rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
+          gv[u] = ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, t, v)) : 0.f;
+          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+        }
 #pragma unroll
         for (int u = 0; u < BN_UB; ++u) {
           if (n + u < n1) {
             float xhat, gs;
-            const float gp = bn_gpre(has_prelu, yv[i][u], rv[i][u], gv[i][u], mv[i][u], mu[i], is[i], g[i], b[i], slope,
-                                     xhat, gs);
+            const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
             a1[i] += gp;
             a2[i] = fmaf(gp, xhat, a2[i]);
             gsl += gs;
@@ -451,45 +423,30 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
     }
   }
   for (int n = n0; n < n1; n += BN_UB) {
-    float yv[NJ][BN_UB], rv[NJ][BN_UB], gv[NJ][BN_UB], mv[NJ][BN_UB];
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-#pragma unroll
-      for (int u = 0; u < BN_UB; ++u) {
-        const bool ok = tt[i] >= 0 && n + u < n1;
-        yv[i][u] = ok ? __ldg(q.y.p + vix(q.y, n + u, c, tt[i], vv[i])) : 0.f;
-        gv[i][u] = (ok && !g_stage) ? __ldg(q.gout.p + vix(q.gout, n + u, c, tt[i], vv[i])) : 0.f;
-        rv[i][u] = (ok && use_r && !r_stage) ? __ldg(q.r.p + vix(q.r, n + u, c, tt[i], vv[i])) : 0.f;
-        mv[i][u] = (ok && q.mask) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + tt[i]) * V + vv[i]) : 1.f;
-      }
-    }
     if (g_stage || r_stage || gr_stage) {
       __syncthreads();
       if (g_stage) stage_planes<NJ, BN_UB>(q.gout, c, n, n1, T, V, shg, TV);
       if (r_stage) stage_planes<NJ, BN_UB>(q.r, c, n, n1, T, V, shr, TV);
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) {
-        if (tt[i] >= 0) {
-          const int e = tt[i] * V + vv[i];
-#pragma unroll
-          for (int u = 0; u < BN_UB; ++u) {
-            if (g_stage) gv[i][u] = shg[u * TV + e];
-            if (r_stage) rv[i][u] = shr[u * TV + e];
-          }
-        }
-      }
     }
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       if (tt[i] >= 0) {
         const int t = tt[i], v = vv[i], e = t * V + v;
+        float yv[BN_UB], rv[BN_UB], gv[BN_UB], mv[BN_UB];
+#pragma unroll
+        for (int u = 0; u < BN_UB; ++u) {
+          const bool ok = n + u < n1;
+          yv[u] = ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f;
+          rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
+          gv[u] = g_stage ? shg[u * TV + e] : (ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, t, v)) : 0.f);
+          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+        }
 #pragma unroll
         for (int u = 0; u < BN_UB; ++u) {
           if (n + u < n1) {
             float xhat, gs;
-            const float gp = bn_gpre(has_prelu, yv[i][u], rv[i][u], gv[i][u], mv[i][u], mu[i], is[i], g[i], b[i], slope,
-                                     xhat, gs);
+            const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
             q.gy.p[vix(q.gy, n + u, c, t, v)] = g[i] * is[i] * (gp - k1[i] - xhat * k2[i]);
             if (q.gr.p) {
               if (gr_stage) sho[u * TV + e] = gp;
