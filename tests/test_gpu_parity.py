@@ -474,3 +474,41 @@ def test_cuda_graph_step_matches_eager():
     sa, sb = m_a.state_dict(), m_b.state_dict()
     for k in sa:
         assert max_abs(sa[k], sb[k]) < 1e-6, k
+
+
+# ================================================================================================= edge cases
+def test_batch_of_one_and_non_contiguous_input():
+    """N=1 (BatchNorm statistics over T only) and a strided input tensor, against the oracle."""
+    from oracle import dstd_oracle as orc
+    torch.manual_seed(5)
+    m = _perturbed(_mod("std").DSTDGCN(6, 4, 6, 0.0, 22, 8, 2, "h36m"))
+    p64 = orc.state_from_module(m, torch.float64)
+    base = torch.randn(1, 22, 10, 3, generator=torch.Generator().manual_seed(9), dtype=torch.float64)
+    x = base.permute(0, 2, 1, 3)                      # [1,10,22,3], non-contiguous
+    x64 = x.clone().requires_grad_(True)
+    y64 = orc.dstdgcn(x64, p64, True, False)
+    y64.pow(2).mean().backward()
+    md = m.to(DEV).train()
+    xd = base.float().to(DEV).permute(0, 2, 1, 3).requires_grad_(True)
+    y = md(xd)
+    y.pow(2).mean().backward()
+    assert rel_err(y, y64) < 1e-4
+    assert rel_err(xd.grad, x64.grad) < 1e-3
+
+
+def test_operator_default_alpha_and_eval_determinism():
+    g = torch.Generator().manual_seed(3)
+    op = _mod("std").DSTDGC(8, 8, 10, 22, mode="spatial").to(DEV)
+    x = torch.randn(2, 8, 10, 22, generator=g).to(DEV)
+    A = torch.rand(1, 22, 22, generator=g).to(DEV)
+    y1 = op(x, A)                                     # alpha_m defaults to the python scalar 1 (dstdgcn.py:80)
+    y2 = op(x, A, torch.ones(1, device=DEV))
+    assert torch.equal(y1, y2)
+    m = _perturbed(_mod("fast").DSTDGCN(6, 4, 6, 0.0, 22, 8, 2, "h36m")).to(DEV)
+    xin = torch.randn(3, 10, 22, 3, generator=g).to(DEV)
+    with torch.no_grad():
+        m.train()
+        m(xin)
+        m.eval()
+        a, b = m(xin), m(xin)
+    assert torch.equal(a, b)                          # fixed-order reductions: bitwise reproducible

@@ -158,3 +158,5 @@ def test_registry_and_errors():
         std.DSTDGC(4, 4, 5, 5, mode="other")
     with pytest.raises(NotImplementedError):
         Graph("nope")
+    with pytest.raises(NotImplementedError):
+        std.DSTDGC(4, 4, 5, 5, red_channels=3)            # the kernels implement the reference's red_channels=2
