@@ -391,6 +391,10 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bytes_pass = algorithmic_bytes_per_pass(v, t)
+        traffic = None      # measured DRAM bytes per step (ncu dram__bytes_read+write over every launch of one step)
+        tpath = os.path.join(ROOT, "profiles", f"r01_dram_traffic_{args.workload}_b{args.batch}.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
         passes_per_s_gpu = 2.0 * sps / world                      # inverse=True: two model passes per sample
         achieved = passes_per_s_gpu * bytes_pass / 1e9
         h2d = sum(x.numel() * 4 for x in host[0])
@@ -404,7 +408,8 @@ def main():
             "gpu_launches": launches, "cuda_graph": not args.no_graph,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": 2 * bytes_pass * args.batch,
                          "scope": "whole training step per GPU: algorithmic bytes = one HBM round trip per DSTDGCB "
                                   f"layer fwd+bwd = {bytes_pass} B per model pass (SURVEY.md 8d), 2 passes per sample",
                          "algorithmic_bytes_per_sample": 2 * bytes_pass},
