@@ -9,6 +9,8 @@
 //
 // Statistics use shifted sums (shift = y[0,c,0,v]) accumulated in fp32 per thread and combined in fp64, so the
 // E[x^2]-E[x]^2 cancellation does not bite on millimetre-scale poses.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace dstd {
@@ -23,7 +25,12 @@ static int bn_ub(int nj) { return nj <= 1 ? 8 : 4; }
 
 int bn_act_splits(int N, int C) {
   (void)C;
-  int s = (N + 7) / 8;            // ~8 samples per CTA (measured: fewer, longer CTAs are slower)
+  static const int per_cta = [] {
+    const char* e = getenv("DSTD_BN_SAMPLES_PER_CTA");     // tuning knob; default measured best on B200
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : v;
+  }();
+  int s = (N + per_cta - 1) / per_cta;
   if (s > 128) s = 128;
   if (s < 1) s = 1;
   return s;
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) 
 using namespace dstd;
 
 extern "C" size_t dstd_bn_act_workspace_bytes(int N, int C, int T, int V) {
-  int S = (N + 7) / 8 > 128 ? 128 : (N + 7) / 8;   // upper bound of bn_act_splits
+  int S = N > 128 ? 128 : N;   // upper bound of bn_act_splits
   if (S < 1) S = 1;
   return arena_need({(size_t)S * C * V * 2 * sizeof(float), (size_t)S * C * sizeof(float)});
 }
