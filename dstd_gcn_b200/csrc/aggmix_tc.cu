@@ -64,8 +64,10 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+constexpr int TC_NT = 512;   // 16 warps per persistent CTA
+
 template <int WH>
-__global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, int KD, int NP, int tmem_cols, int* err_flag) {
+__global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q, int KD, int NP, int tmem_cols, int* err_flag) {
   extern __shared__ __align__(16) float smem[];
   constexpr int KP = 2 * WH;
   const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, Cout = q.Cout, nb = q.nb, PCH = q.PCH;
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
   // ---- once per CTA: resident weights, static adjacency, zeroed A tiles (pad rows of K must read as 0), TMEM, mbarrier
   {
     const int n4 = nb * 2 * b_tile_f / 4;
-    for (int i = tid; i < n4; i += 256) cp_async16(b_img + 4 * i, q.wtc + 4 * i);
-    for (int i = tid; i < 2 * a_tile_f; i += 256) a_hi[i] = 0.f;
-    for (int i = tid; i < nb * KK; i += 256) {
+    for (int i = tid; i < n4; i += TC_NT) cp_async16(b_img + 4 * i, q.wtc + 4 * i);
+    for (int i = tid; i < 2 * a_tile_f; i += TC_NT) a_hi[i] = 0.f;
+    for (int i = tid; i < nb * KK; i += TC_NT) {
       const int b = i / KK, e = i - b * KK;
       float a = __ldg(q.adj[b] + e);
       if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + e);
@@ -141,14 +143,14 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
         poff[i] = j < npos ? (int)(l * q.x.sp + k * q.x.sk) : -1;
       }
       const float* xb = q.x.p + (long long)n * q.x.sn + (long long)p0 * q.x.sp;
-      for (int c = warp; c < Cin; c += 8) {
+      for (int c = warp; c < Cin; c += TC_NT / 32) {
 #pragma unroll
         for (int i = 0; i < TNS; ++i)
           if (poff[i] >= 0) cp_async4(xs + c * XS_LD + lane + 32 * i, xb + (long long)c * q.x.sc + poff[i], true);
       }
       for (int b = 0; b < nb; ++b) {
         const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
-        for (int i = tid; i < pv * KK; i += 256) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+        for (int i = tid; i < pv * KK; i += TC_NT) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
       }
       if (q.skip.p) {
         // lane order (k major, l minor) when the skip is contiguous along p, else the position order
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
           sdst[i] = l * K + k;
         }
         const float* sb = q.skip.p + (long long)n * q.skip.sn + (long long)p0 * q.skip.sp;
-        for (int o = warp; o < Cout; o += 8) {
+        for (int o = warp; o < Cout; o += TC_NT / 32) {
 #pragma unroll
           for (int i = 0; i < TNS; ++i)
             if (soff[i] >= 0) cp_async4(sks + o * XS_LD + sdst[i], sb + (long long)o * q.skip.sc + soff[i], true);
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
       }
       cp_async_wait_all();
       __syncthreads();
-      for (int i = tid; i < nb * PCH * K * KP; i += 256) {
+      for (int i = tid; i < nb * PCH * K * KP; i += TC_NT) {
         int w = i % KP, t = i / KP;
         int v = t % K;
         t /= K;
@@ -188,18 +190,18 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
 
     // ---- 2. per branch: aggregation into the UMMA A tile, then the tensor-core channel mix
     for (int b = 0; b < nb; ++b) {
-      for (int it = warp; it < 2 * pv; it += 8) {
-        const int l = it >> 1, half = it & 1;
+      for (int it = warp; it < 4 * pv; it += TC_NT / 32) {   // item = (frame, w half, channel half); lane = channel
+        const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
         const float* xm_l = xms + ((b * PCH + l) * K) * KP + half * WH;
         for (int cg = 0; cg < Cin; cg += 64) {
-          const int c0 = cg + lane, c1 = c0 + 32;
+          const int c0 = cg + chalf * 32 + lane;
           const float* x0p = xs + min(c0, Cin - 1) * XS_LD + l * K;
-          const float* x1p = xs + min(c1, Cin - 1) * XS_LD + l * K;
-          float a0[WH], a1[WH];
+          float a0[WH];
 #pragma unroll
-          for (int j = 0; j < WH; ++j) a0[j] = a1[j] = 0.f;
+          for (int j = 0; j < WH; ++j) a0[j] = 0.f;
+#pragma unroll 2
           for (int v = 0; v < K; ++v) {
-            const float x0 = x0p[v], x1 = x1p[v];
+            const float x0 = x0p[v];
             const float4* r4 = reinterpret_cast<const float4*>(xm_l + v * KP);
 #pragma unroll
             for (int j4 = 0; j4 < WH / 4; ++j4) {
@@ -208,34 +210,23 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
               a0[j4 * 4 + 1] = fmaf(x0, m.y, a0[j4 * 4 + 1]);
               a0[j4 * 4 + 2] = fmaf(x0, m.z, a0[j4 * 4 + 2]);
               a0[j4 * 4 + 3] = fmaf(x0, m.w, a0[j4 * 4 + 3]);
-              a1[j4 * 4 + 0] = fmaf(x1, m.x, a1[j4 * 4 + 0]);
-              a1[j4 * 4 + 1] = fmaf(x1, m.y, a1[j4 * 4 + 1]);
-              a1[j4 * 4 + 2] = fmaf(x1, m.z, a1[j4 * 4 + 2]);
-              a1[j4 * 4 + 3] = fmaf(x1, m.w, a1[j4 * 4 + 3]);
             }
           }
+          if (c0 < Cin) {
 #pragma unroll
-          for (int j = 0; j < WH; ++j) {
-            const int w = half * WH + j;
-            if (w < K) {
-              const int pos = l * K + w;
-              float hi, lo;
-              if (c0 < Cin) {
+            for (int j = 0; j < WH; ++j) {
+              const int w = half * WH + j;
+              if (w < K) {
+                float hi, lo;
                 split_tf32(a0[j], hi, lo);
-                const int o = tc_off(pos, c0, sbo_f);
-                a_hi[o] = hi;
-                a_lo[o] = lo;
-              }
-              if (c1 < Cin) {
-                split_tf32(a1[j], hi, lo);
-                const int o = tc_off(pos, c1, sbo_f);
+                const int o = tc_off(l * K + w, c0, sbo_f);
                 a_hi[o] = hi;
                 a_lo[o] = lo;
               }
             }
           }
         }
-        if (lane < WH && half * WH + lane < K) {   // ones row (K index Cin): column sums of xm carry the conv_f bias
+        if (chalf == 0 && lane < WH && half * WH + lane < K) {   // ones row (K index Cin): column sums of xm carry the bias
           float s = 0.f;
           for (int v = 0; v < K; ++v) s += xm_l[v * KP + lane];
           float hi, lo;
@@ -269,29 +260,26 @@ __global__ void __launch_bounds__(256, 1) aggmix_fwd_tc_kernel(AggMixParams q, i
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 
-    // ---- 3. epilogue: TMEM -> registers -> out (+ skip).  warp w: lanes 32 (w%4) .. +31 (positions), columns 32 (w/4) ..
+    // ---- 3. epilogue: TMEM -> registers -> out (+ skip).  warp w: lanes 32 (w%4) .. +31 (positions), columns 16 (w/4) ..
     {
       const int pos = (warp & 3) * 32 + lane;
       const int l = pos / K, k = pos - l * K;
       const bool pok = pos < npos;
       const long long off_o = (long long)n * q.out.sn + (long long)(p0 + l) * q.out.sp + (long long)k * q.out.sk;
-      for (int col0 = (warp >> 2) * 32; col0 < NP; col0 += 64) {
-        uint32_t r[32];
+      for (int col0 = (warp >> 2) * 16; col0 < NP; col0 += 64) {
+        uint32_t r[16];
         const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (pok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const int o = col0 + j;
             if (o < Cout) {
               float v = ok ? __uint_as_float(r[j]) : __int_as_float(0x7fc00000);   // a stalled pipeline must be loud
@@ -348,7 +336,7 @@ static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g, bool wit
   g.tmem_cols = g.NP <= 32 ? 32 : 64;
   const int KP = 2 * g.WH, sbo_f = (g.KD / 4) * TC_LBO_F;
   g.wtc_floats = (size_t)nb * 2 * (g.NP / 8) * sbo_f;
-  for (int pch = 128 / K; pch >= 1; --pch) {
+  for (int pch = (128 / K >= 4 ? 4 : 128 / K); pch >= 1; --pch) {   // 4 frames = 16 aggregation items = 16 warps
     if (pch > P && pch > 1) continue;
     const int XS_LD = (pch * K) | 1;
     size_t f = (size_t)2 * ((pch * K + 7) / 8) * sbo_f + g.wtc_floats + (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * pch * K * KP +
@@ -398,7 +386,7 @@ int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cu
   if (g.WH == WH_) {                                                                        \
     auto kern = aggmix_fwd_tc_kernel<WH_>;                                                  \
     ensure_max_smem((const void*)kern);                                                     \
-    kern<<<ctas, 256, g.smem, st>>>(q, g.KD, g.NP, g.tmem_cols, err_flag);                  \
+    kern<<<ctas, TC_NT, g.smem, st>>>(q, g.KD, g.NP, g.tmem_cols, err_flag);                  \
   }
   DSTD_AMTC(12) DSTD_AMTC(16) DSTD_AMTC(20)
 #undef DSTD_AMTC
