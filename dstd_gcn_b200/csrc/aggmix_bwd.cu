@@ -68,6 +68,13 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   }
   const int o0 = (warp & 7) * 8;
 
+  // optional per-phase cycle counters (-DDSTD_PHASE_TIMING, printed by CTA 0): how the optimisation targets were picked
+#ifdef DSTD_PHASE_TIMING
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define PH(i) do { __syncthreads(); long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define PH(i) do {} while (0)
+#endif
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int n = (int)(item / nchunk), p0 = (int)(item - (long long)n * nchunk) * PCH;
     const int pv = min(PCH, P - p0);
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       }
       cp_async_wait_all();
       __syncthreads();
+      PH(0);
       for (int i = tid; i < nb * PCH * K * KP2; i += AMB_NT) {
         int w = i % KP2, t = i / KP2;
         int v = t % K;
@@ -127,6 +135,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       }
     }
     __syncthreads();
+    PH(1);
 
 #pragma unroll
     for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {   // unrolled: accw[b] must stay in registers
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
         }
       }
 
+      PH(2);
       // ================= (b) xa_b recompute    (warp = (frame, w half, channel half), lane = channel)
       for (int it = warp; it < 4 * pv; it += AMB_NT / 32) {
         const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
@@ -237,6 +247,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       }
       __syncthreads();
 
+      PH(3);
       // ================= (c) weight gradient: accw[b][r][i] += sum_pos gout[o0+r][pos] xa_b[lane+32i][pos]
       if (o0 < Cout) {
         const int j0c = min(lane, Cin - 1), j1c = min(lane + 32, Cin - 1);
@@ -272,6 +283,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
         accb[b] += s;
       }
 
+      PH(4);
       // ================= (d) gx += gxa_b xmu_b^T    (warp = (frame, v half, channel half), lane = channel)
       for (int it = warp; it < 4 * pv; it += AMB_NT / 32) {
         const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
@@ -314,6 +326,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
         }
       }
 
+      PH(5);
       // ================= (e) gxmu_b[l][v][w] = sum_{c<=Cin} xaug[c][l,v] gxa_b[c][l,w]   (4x4 tiles) -> HBM
       {
         constexpr int NT4 = KP / 4;
@@ -354,6 +367,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
         }
       }
       __syncthreads();   // gxas / xas are rewritten by the next branch
+      PH(6);
     }
 
     // ---- gx chunk -> HBM (coalesced along the contiguous (l,k) run of each channel)
@@ -368,6 +382,12 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
     }
   }
 
+  PH(7);
+#ifdef DSTD_PHASE_TIMING
+  if (blockIdx.x == 0 && tid == 0)
+    printf("aggmix_bwd phases (cycles, CTA 0): stage %lld transform %lld a %lld b %lld c %lld d %lld e %lld tail %lld\n",
+           tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7]);
+#endif
   // ---- per-CTA partials of the conv_f gradients
   float* pw = q.part_w + ((long long)blockIdx.x * 2 + (warp >> 3)) * nb * Cout * Cin;
   float* pb = q.part_b + (long long)blockIdx.x * nb * Cout;
