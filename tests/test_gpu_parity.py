@@ -111,6 +111,20 @@ def test_gc_unit_abi(case):
             assert max_abs(gr[b][key], ref) < 1e-4 * max(1.0, float(ref.abs().max())), (b, key)
 
 
+@pytest.mark.parametrize("case", [GC_CASES[2], GC_CASES[3], GC_CASES[6]], ids=["enc_spatial", "temporal_skip", "fast"])
+def test_gc_unit_abi_cuda_core_forward(case, monkeypatch):
+    """Same checks with the tcgen05 forward kernel switched off: the CUDA-core fused forward kernel stays covered."""
+    monkeypatch.setenv("DSTD_DISABLE_TC", "1")
+    test_gc_unit_abi(case)
+
+
+def test_gc_unit_abi_wide_channels_unfused_path():
+    """Cin, Cout > 64: outside the fused kernels' tile limits -> aggregate + bgemm + wgrad path that keeps xa."""
+    test_gc_unit_abi((2, 80, 72, 12, 22, 2, "pk", False, True))
+    assert _lib.load_library().dstd_gc_needs_xa(80, 72, 12, 22, 2) == 1
+    assert _lib.load_library().dstd_gc_needs_xa(64, 64, 35, 22, 2) == 0
+
+
 def test_gc_unit_errors():
     be = cuda_backend()
     g = torch.Generator().manual_seed(5)
