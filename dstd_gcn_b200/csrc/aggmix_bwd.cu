@@ -16,6 +16,21 @@
 
 namespace dstd {
 
+// ---- legacy tensor path (mma.sync m16n8k8 TF32, operands in registers) with 3xTF32 error compensation.  The two channel
+// GEMMs of this kernel were limited by the shared-memory return path on CUDA cores (every operand value costs a
+// 4-byte-per-lane delivery: 11 deliveries per 24 FMAs at the 8x3 register tile the 128-register budget allows); with
+// mma.sync each delivered value feeds 64-128 MACs.  tcgen05 would need hi/lo operand images in shared memory that do
+// not fit next to the frame-chunk tiles.
+__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 constexpr int AMB_NT = 512;   // 16 warps; the two channel GEMMs are split 2-way along their reduction dimension
 
 template <int KP, int TN>
@@ -28,13 +43,15 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   const int npos_pad = PCH * KP;
   float* xs = smem;                         // [C1][LD]    (row Cin = ones on valid positions)
   float* gos = xs + C1 * LD;                // [Cout][LD]
-  float* gxas = gos + Cout * LD;            // [C1][LD]
+  const int CoutR8 = (Cout + 7) & ~7, CoutR16 = (Cout + 15) & ~15;
+  const int WS = q.WS;                      // weight row stride: >= round16(Cin), == 8 (mod 32)
+  float* gxas = gos + CoutR16 * LD;         // [C1][LD]
   float* xas = gxas + C1 * LD;              // [C1][LD]
   float* gxs = xas + C1 * LD;               // [Cin][LD]
   float* xms = gxs + Cin * LD;              // [nb][PCH][K][KP2]   xmu[l][v][w]
   float* xmT = xms + nb * PCH * K * KP2;    // [nb][PCH][K][KP2]   xmu[l][w][v]
-  float* wfB = xmT + nb * PCH * K * KP2;    // [nb][Cout][CinP]
-  float* bfs = wfB + nb * Cout * CinP;      // [nb][Cout]
+  float* wfB = xmT + nb * PCH * K * KP2;    // [nb][CoutR8][WS]   (zero padded)
+  float* bfs = wfB + nb * CoutR8 * WS;      // [nb][Cout]
   float* aeff = bfs + ((nb * Cout + 3) & ~3);   // [nb][K*K]    static adjacency A*W + R
   float* pdr = aeff + ((nb * KK + 3) & ~3);     // [nb][PCH][K*K] raw dynamic adjacency of the current item
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -43,11 +60,14 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   const long long nitems = (long long)q.N * nchunk;
 
   // ---- once per CTA: weights
-  for (int i = tid; i < nb * Cout * CinP; i += AMB_NT) {
-    int c = i % CinP, t = i / CinP;
-    int o = t % Cout, b = t / Cout;
-    wfB[i] = c < Cin ? __ldg(q.w_f[b] + (long long)o * Cin + c) : 0.f;
+  for (int i = tid; i < nb * CoutR8 * WS; i += AMB_NT) {
+    int c = i % WS, t = i / WS;
+    int o = t % CoutR8, b = t / CoutR8;
+    wfB[i] = (c < Cin && o < Cout) ? __ldg(q.w_f[b] + (long long)o * Cin + c) : 0.f;
   }
+  // rows / columns that the 8- and 16-wide MMA tiles read beyond the data must be zero (K padding) for the whole kernel
+  for (int i = tid; i < CoutR16 * LD; i += AMB_NT) gos[i] = 0.f;
+  for (int i = tid; i < C1 * LD; i += AMB_NT) xas[i] = 0.f;
   for (int i = tid; i < nb * Cout; i += AMB_NT) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
   for (int i = tid; i < nb * KK; i += AMB_NT) {
     const int b = i / KK, e = i - b * KK;
@@ -58,15 +78,21 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   }
 
   // persistent weight-gradient accumulators: warp = 8 output channels, lane = input channels (lane, lane+32)
-  float accw[DSTD_MAX_BRANCH][8][2];
+  // persistent weight-gradient accumulators: warp = one 16-row tile of o x two 8-column tiles of j (mma C fragments)
+  float accw[DSTD_MAX_BRANCH][2][4];
   float accb[DSTD_MAX_BRANCH];
 #pragma unroll
   for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
     accb[b] = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) accw[b][r][0] = accw[b][r][1] = 0.f;
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) accw[b][i][r] = 0.f;
   }
-  const int o0 = (warp & 7) * 8;
+  const int fg = lane >> 2, ft = lane & 3;               // mma fragment coordinates
+  const int MTo = CoutR16 >> 4, NTj = (Cin + 7) >> 3;    // tiles of the gradient matrix [o][j]
+  const int c_mi = warp % MTo, c_np = warp / MTo;        // this warp's tiles in (c): m-tile, pair of n-tiles
+  const bool c_act = 2 * c_np < NTj;
 
   // optional per-phase cycle counters (-DDSTD_PHASE_TIMING, printed by CTA 0): how the optimisation targets were picked
 #ifdef DSTD_PHASE_TIMING
@@ -140,59 +166,50 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
 #pragma unroll
     for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {   // unrolled: accw[b] must stay in registers
       if (b >= nb) break;
-      // ================= (a) gxa_b = wcat_b^T gout    (warp = 8 rows j x half of the o range, lane = positions;
-      //                   the two halves are combined through gxas)
+      // ================= (a) gxa_b = wcat_b^T gout on mma.sync (3xTF32): D[j][pos] = sum_o W[o][j] g[o][pos]
+      //                   warp = one 16-row tile of j x TN 8-column tiles of positions, K = o in steps of 8
       {
-        const int ks = warp >> 3, j0 = (warp & 7) * 8;
-        const int oh = (Cout + 1) >> 1, ob = ks * oh, oe = min(Cout, ob + oh);
-        const bool act = j0 < Cin;
-        float acc[8][TN];
+        const int MT = (Cin + 15) >> 4, NTt = (npos_pad + 7) >> 3, NG = (NTt + TN - 1) / TN;
+        const float* wb = wfB + b * CoutR8 * WS;
+        for (int grp = warp; grp < MT * NG; grp += AMB_NT / 32) {
+          const int m0 = (grp % MT) * 16, n0 = (grp / MT) * TN * 8;
+          float acc[TN][4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+          for (int i = 0; i < TN; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+          for (int k0 = 0; k0 < CoutR8; k0 += 8) {
+            const float* wr = wb + (k0 + ft) * WS + m0 + fg;
+            uint32_t ah[4], al[4];
+            split3(wr[0], ah[0], al[0]);
+            split3(wr[8], ah[1], al[1]);
+            split3(wr[4 * WS], ah[2], al[2]);
+            split3(wr[4 * WS + 8], ah[3], al[3]);
+            const float* gr = gos + (k0 + ft) * LD + n0 + fg;
 #pragma unroll
-          for (int i = 0; i < TN; ++i) acc[r][i] = 0.f;
-        if (act) {
-          const float* wrow = wfB + (b * Cout) * CinP + j0;
-#pragma unroll 2
-          for (int o = ob; o < oe; ++o) {
-            const float4 wa = *reinterpret_cast<const float4*>(wrow + o * CinP);
-            const float4 wb = *reinterpret_cast<const float4*>(wrow + o * CinP + 4);
-            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-            float gv[TN];
-#pragma unroll
-            for (int i = 0; i < TN; ++i) gv[i] = gos[o * LD + lane + 32 * i];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-              for (int i = 0; i < TN; ++i) acc[r][i] = fmaf(wv[r], gv[i], acc[r][i]);
-          }
-        }
-        if (ks == 1) {
-          if (act) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-              if (j0 + r < Cin) {
-#pragma unroll
-                for (int i = 0; i < TN; ++i)
-                  if (lane + 32 * i < npos_pad) gxas[(j0 + r) * LD + lane + 32 * i] = acc[r][i];
-              }
-          }
-          // bias row: gxa[Cin][pos] = sum_o bf[o] gout[o][pos]
-          for (int pos = tid - 256; pos < npos_pad; pos += 256) {
-            float sres = 0.f;
-            for (int o = 0; o < Cout; ++o) sres = fmaf(bfs[b * Cout + o], gos[o * LD + pos], sres);
-            gxas[Cin * LD + pos] = sres;
-          }
-        }
-        __syncthreads();
-        if (ks == 0 && act) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (j0 + r < Cin) {
-#pragma unroll
-              for (int i = 0; i < TN; ++i)
-                if (lane + 32 * i < npos_pad) gxas[(j0 + r) * LD + lane + 32 * i] += acc[r][i];
+            for (int i = 0; i < TN; ++i) {
+              uint32_t bh[2], bl[2];
+              split3(gr[i * 8], bh[0], bl[0]);
+              split3(gr[i * 8 + 4 * LD], bh[1], bl[1]);
+              mma_tf32(acc[i], ah, bh);
+              mma_tf32(acc[i], ah, bl);
+              mma_tf32(acc[i], al, bh);
             }
+          }
+#pragma unroll
+          for (int i = 0; i < TN; ++i) {
+            const int col = n0 + i * 8 + 2 * ft;
+            if (col < npos_pad) {
+              if (m0 + fg < Cin) *reinterpret_cast<float2*>(gxas + (m0 + fg) * LD + col) = make_float2(acc[i][0], acc[i][1]);
+              if (m0 + fg + 8 < Cin)
+                *reinterpret_cast<float2*>(gxas + (m0 + fg + 8) * LD + col) = make_float2(acc[i][2], acc[i][3]);
+            }
+          }
+        }
+        // bias row: gxa[Cin][pos] = sum_o bf[o] gout[o][pos]   (warp = positions, lanes = output channels)
+        for (int pos = warp; pos < npos_pad; pos += AMB_NT / 32) {
+          float sres = 0.f;
+          for (int o = lane; o < Cout; o += 32) sres = fmaf(bfs[b * Cout + o], gos[o * LD + pos], sres);
+          sres = warp_sum(sres);
+          if (lane == 0) gxas[Cin * LD + pos] = sres;
         }
       }
 
@@ -248,29 +265,30 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       __syncthreads();
 
       PH(3);
-      // ================= (c) weight gradient: accw[b][r][i] += sum_pos gout[o0+r][pos] xa_b[lane+32i][pos]
-      if (o0 < Cout) {
-        const int j0c = min(lane, Cin - 1), j1c = min(lane + 32, Cin - 1);
-        const int nr = min(8, Cout - o0);
-        const int phalf = ((npos_pad / 4 + 1) / 2) * 4;          // the two warp groups split the positions
-        const int pb = (warp >> 3) * phalf, pe = (warp >> 3) ? npos_pad : phalf;
-        for (int p4 = pb; p4 < pe; p4 += 4) {
-          const float4 b0 = *reinterpret_cast<const float4*>(xas + j0c * LD + p4);
-          const float4 b1 = *reinterpret_cast<const float4*>(xas + j1c * LD + p4);
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            if (r < nr) {
-              const float4 a = *reinterpret_cast<const float4*>(gos + (o0 + r) * LD + p4);
-              accw[b][r][0] = fmaf(a.x, b0.x, accw[b][r][0]);
-              accw[b][r][0] = fmaf(a.y, b0.y, accw[b][r][0]);
-              accw[b][r][0] = fmaf(a.z, b0.z, accw[b][r][0]);
-              accw[b][r][0] = fmaf(a.w, b0.w, accw[b][r][0]);
-              accw[b][r][1] = fmaf(a.x, b1.x, accw[b][r][1]);
-              accw[b][r][1] = fmaf(a.y, b1.y, accw[b][r][1]);
-              accw[b][r][1] = fmaf(a.z, b1.z, accw[b][r][1]);
-              accw[b][r][1] = fmaf(a.w, b1.w, accw[b][r][1]);
-            }
-          }
+      // ================= (c) weight gradient on mma.sync (3xTF32): G[o][j] += sum_pos gout[o][pos] xa_b[j][pos]
+      if (c_act) {
+        const int m0 = c_mi * 16;
+        const float* ar = gos + (m0 + fg) * LD + ft;
+        const float* br0 = xas + min((2 * c_np) * 8 + fg, Cin) * LD + ft;
+        const float* br1 = xas + min((2 * c_np + 1) * 8 + fg, Cin) * LD + ft;
+        const int ksteps = (npos_pad + 7) >> 3;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int k0 = ks * 8;
+          uint32_t ah[4], al[4], bh[2], bl[2];
+          split3(ar[k0], ah[0], al[0]);
+          split3(ar[k0 + 8 * LD], ah[1], al[1]);
+          split3(ar[k0 + 4], ah[2], al[2]);
+          split3(ar[k0 + 8 * LD + 4], ah[3], al[3]);
+          split3(br0[k0], bh[0], bl[0]);
+          split3(br0[k0 + 4], bh[1], bl[1]);
+          mma_tf32(accw[b][0], ah, bh);
+          mma_tf32(accw[b][0], ah, bl);
+          mma_tf32(accw[b][0], al, bh);
+          split3(br1[k0], bh[0], bl[0]);
+          split3(br1[k0 + 4], bh[1], bl[1]);
+          mma_tf32(accw[b][1], ah, bh);
+          mma_tf32(accw[b][1], ah, bl);
+          mma_tf32(accw[b][1], al, bh);
         }
       }
       if (tid < Cout) {   // bias gradient: sum_pos gout[o][pos] * (column sums of xmu)
@@ -389,17 +407,23 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
            tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7]);
 #endif
   // ---- per-CTA partials of the conv_f gradients
-  float* pw = q.part_w + ((long long)blockIdx.x * 2 + (warp >> 3)) * nb * Cout * Cin;
+  float* pw = q.part_w + (long long)blockIdx.x * nb * Cout * Cin;
   float* pb = q.part_b + (long long)blockIdx.x * nb * Cout;
 #pragma unroll
   for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
     if (b < nb) {
+      if (c_act) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int o = o0 + r;
-        if (o < Cout) {
-          if (lane < Cin) pw[((long long)b * Cout + o) * Cin + lane] = accw[b][r][0];
-          if (lane + 32 < Cin) pw[((long long)b * Cout + o) * Cin + lane + 32] = accw[b][r][1];
+        for (int i = 0; i < 2; ++i) {
+          const int j = (2 * c_np + i) * 8 + 2 * ft;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int o = c_mi * 16 + fg + 8 * h;
+            if (o < Cout) {
+              if (j < Cin) pw[((long long)b * Cout + o) * Cin + j] = accw[b][i][2 * h];
+              if (j + 1 < Cin) pw[((long long)b * Cout + o) * Cin + j + 1] = accw[b][i][2 * h + 1];
+            }
+          }
         }
       }
       if (tid < Cout) pb[b * Cout + tid] = accb[b];
@@ -409,7 +433,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
 
 // ------------------------------------------------------------------------------------------ launch
 struct AggMixBwdGeom {
-  int KP, TN, PCH, LD, CinP;
+  int KP, TN, PCH, LD, CinP, WS;
   size_t smem;
 };
 
@@ -418,12 +442,16 @@ static bool aggmix_bwd_geom(int Cin, int Cout, int P, int K, int nb, AggMixBwdGe
   g.KP = K <= 24 ? 24 : K <= 28 ? 28 : K <= 36 ? 36 : 40;
   const int WH = (g.KP / 2 + 3) / 4 * 4, KP2 = 2 * WH, C1 = Cin + 1;
   g.CinP = (Cin + 7) / 8 * 8;
+  g.WS = (Cin + 15) / 16 * 16;
+  while (g.WS % 32 != 8) g.WS += 8;          // conflict-free A-fragment loads: row stride == 8 (mod 32)
+  const int CoutR8 = (Cout + 7) / 8 * 8, CoutR16 = (Cout + 15) / 16 * 16;
+  if ((CoutR16 / 16) * ((Cin + 15) / 16) > AMB_NT / 32) return false;   // (c): one warp per (16 x 16) gradient tile pair
   for (int pch = 128 / g.KP; pch >= 1; --pch) {
     if (pch > P && pch > 1) continue;
     const int npad = pch * g.KP;
     int ld = npad + 4;
     if ((ld / 4) % 2 == 0) ld += 4;
-    size_t f = (size_t)(3 * C1 + Cout + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * Cout * g.CinP +
+    size_t f = (size_t)(3 * C1 + CoutR16 + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * CoutR8 * g.WS +
                (size_t)nb * Cout + (size_t)nb * K * K * (pch + 1) + 32;
     if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 512) {
       g.PCH = pch;
@@ -453,7 +481,7 @@ int launch_aggmix_bwd(AggMixBwdParams q, cudaStream_t st) {
   AggMixBwdGeom g;
   DSTD_REQUIRE(aggmix_bwd_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g), DSTD_ERR_UNSUPPORTED,
                "aggmix_bwd: Cin=%d Cout=%d K=%d outside the compiled tile limits", q.Cin, q.Cout, q.K);
-  q.PCH = g.PCH; q.LD = g.LD; q.CinP = g.CinP;
+  q.PCH = g.PCH; q.LD = g.LD; q.CinP = g.CinP; q.WS = g.WS;
   const int ctas = aggmix_bwd_ctas(q.N, q.P, q.K, q.Cin, q.Cout, q.nb);
 #define DSTD_AMB(KP_, TN_)                                           \
   if (g.KP == KP_ && g.TN == TN_) {                                  \

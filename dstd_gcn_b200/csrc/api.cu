@@ -232,7 +232,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
     AggMixBwdParams am;
     am.N = N; am.Cin = Cin; am.Cout = Cout; am.P = P; am.K = K; am.nb = nb;
     am.adj_t = (a->flags & DSTD_FLAG_ADJ_T) ? 1 : 0;
-    am.PCH = am.LD = am.CinP = 0;
+    am.PCH = am.LD = am.CinP = am.WS = 0;
     am.x = mk(a->x); am.gout = mk(a->gout); am.gx = mk(a->gx);
     am.pd = a->pd; am.alpha = a->alpha;
     for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
@@ -323,7 +323,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   for (int b = 0; b < nb; ++b) {
     const dstd_branch_grad& g = a->gbr[b];
     if (fused) {
-      seg(p_wf + (long long)b * Cout * Cin, 2 * n_wf, (long long)nb * Cout * Cin, Cout, Cin, Cin, g.w_f, Cin);
+      seg(p_wf + (long long)b * Cout * Cin, n_wf, (long long)nb * Cout * Cin, Cout, Cin, Cin, g.w_f, Cin);
       seg(p_bf + (long long)b * Cout, n_wf, (long long)nb * Cout, Cout, 1, 1, g.b_f, 1);
     } else {
       seg(p_wcat + b * C1, S1a, st_wcat, Cout, Cin, nb * C1, g.w_f, Cin);

@@ -147,7 +147,7 @@ int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cu
 // ------------------------------------------------------------------ aggmix_bwd.cu
 struct AggMixBwdParams {
   int N, Cin, Cout, P, K, nb, adj_t;
-  int PCH, LD, CinP;   // filled by the launcher
+  int PCH, LD, CinP, WS;   // filled by the launcher
   View4 x;             // [N,Cin,P,K]
   View4 gout;          // [N,Cout,P,K]
   View4 gx;            // [N,Cin,P,K] written (aggregation part of the input gradient)
