@@ -41,12 +41,13 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, C1 = Cin + 1, Cout = q.Cout, nb = q.nb, PCH = q.PCH;
   const int LD = q.LD, CinP = q.CinP;
   const int npos_pad = PCH * KP;
-  float* xs = smem;                         // [C1][LD]    (row Cin = ones on valid positions)
-  float* gos = xs + C1 * LD;                // [Cout][LD]
+  const int C1R8 = (C1 + 7) & ~7;
+  float* xs = smem;                         // [C1R8][LD]  (row Cin = ones on valid positions, rows above: zero)
+  float* gos = xs + C1R8 * LD;              // [CoutR16][LD]
   const int CoutR8 = (Cout + 7) & ~7, CoutR16 = (Cout + 15) & ~15;
   const int WS = q.WS;                      // weight row stride: >= round16(Cin), == 8 (mod 32)
-  float* gxas = gos + CoutR16 * LD;         // [C1][LD]
-  float* xas = gxas + C1 * LD;              // [C1][LD]
+  float* gxas = gos + CoutR16 * LD;         // [C1R8][LD]  (rows above Cin: zero)
+  float* xas = gxas + C1R8 * LD;            // [C1][LD]
   float* gxs = xas + C1 * LD;               // [Cin][LD]
   float* xms = gxs + Cin * LD;              // [nb][PCH][K][KP2]   xmu[l][v][w]
   float* xmT = xms + nb * PCH * K * KP2;    // [nb][PCH][K][KP2]   xmu[l][w][v]
@@ -68,6 +69,10 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   // rows / columns that the 8- and 16-wide MMA tiles read beyond the data must be zero (K padding) for the whole kernel
   for (int i = tid; i < CoutR16 * LD; i += AMB_NT) gos[i] = 0.f;
   for (int i = tid; i < C1 * LD; i += AMB_NT) xas[i] = 0.f;
+  for (int i = tid; i < (C1R8 - C1) * LD; i += AMB_NT) {
+    xs[C1 * LD + i] = 0.f;
+    gxas[C1 * LD + i] = 0.f;
+  }
   for (int i = tid; i < nb * Cout; i += AMB_NT) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
   for (int i = tid; i < nb * KK; i += AMB_NT) {
     const int b = i / KK, e = i - b * KK;
@@ -214,47 +219,54 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       }
 
       PH(2);
-      // ================= (b) xa_b recompute    (warp = (frame, w half, channel half), lane = channel)
-      for (int it = warp; it < 4 * pv; it += AMB_NT / 32) {
-        const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
-        const float* xm_l = xms + ((b * PCH + l) * K) * KP2 + half * WH;
-        for (int cg = 0; cg < Cin; cg += 64) {
-          const int c0 = cg + chalf * 32 + lane;
-          const bool v0ok = c0 < Cin;
-          float x0[KP];
+      // ================= (b) xa_b recompute on mma.sync: xa[c][l,w] = sum_v x[c][l,v] xmu_b[l][v][w]
+      //                   warp = (frame, 16-channel tile), all w tiles; K = v, last step masked at v >= K
+      {
+        constexpr int NTW = KP2 / 8;
+        const int MTc = (Cin + 15) >> 4;
+        for (int grp = warp; grp < pv * MTc; grp += AMB_NT / 32) {
+          const int l = grp / MTc, m0 = (grp % MTc) * 16;
+          float acc[NTW][4];
 #pragma unroll
-          for (int i = 0; i < KP / 4; ++i) {
-            const float4 t0 = *reinterpret_cast<const float4*>(xs + (v0ok ? c0 : 0) * LD + l * KP + 4 * i);
-            x0[4 * i] = t0.x; x0[4 * i + 1] = t0.y; x0[4 * i + 2] = t0.z; x0[4 * i + 3] = t0.w;
-          }
-          float a0[WH];
+          for (int i = 0; i < NTW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+          const float* ar = xs + (m0 + fg) * LD + l * KP + ft;
+          const float* br = xms + ((b * PCH + l) * K + ft) * KP2 + fg;
+          for (int k0 = 0; k0 < K; k0 += 8) {
+            const bool k_lo = k0 + ft < K, k_hi = k0 + ft + 4 < K;
+            uint32_t ah[4], al[4];
+            split3(k_lo ? ar[k0] : 0.f, ah[0], al[0]);
+            split3(k_lo ? ar[k0 + 8 * LD] : 0.f, ah[1], al[1]);
+            split3(k_hi ? ar[k0 + 4] : 0.f, ah[2], al[2]);
+            split3(k_hi ? ar[k0 + 8 * LD + 4] : 0.f, ah[3], al[3]);
 #pragma unroll
-          for (int j = 0; j < WH; ++j) a0[j] = 0.f;
-#pragma unroll
-          for (int v = 0; v < KP; ++v) {
-            if (v < K) {
-              const float4* r4 = reinterpret_cast<const float4*>(xm_l + v * KP2);
-#pragma unroll
-              for (int j4 = 0; j4 < WH / 4; ++j4) {
-                const float4 m = r4[j4];
-                a0[j4 * 4 + 0] = fmaf(x0[v], m.x, a0[j4 * 4 + 0]);
-                a0[j4 * 4 + 1] = fmaf(x0[v], m.y, a0[j4 * 4 + 1]);
-                a0[j4 * 4 + 2] = fmaf(x0[v], m.z, a0[j4 * 4 + 2]);
-                a0[j4 * 4 + 3] = fmaf(x0[v], m.w, a0[j4 * 4 + 3]);
-              }
+            for (int i = 0; i < NTW; ++i) {
+              uint32_t bh[2], bl[2];
+              split3(k_lo ? br[k0 * KP2 + i * 8] : 0.f, bh[0], bl[0]);
+              split3(k_hi ? br[(k0 + 4) * KP2 + i * 8] : 0.f, bh[1], bl[1]);
+              mma_tf32(acc[i], ah, bh);
+              mma_tf32(acc[i], ah, bl);
+              mma_tf32(acc[i], al, bh);
             }
           }
 #pragma unroll
-          for (int j4 = 0; j4 < WH / 4; ++j4) {
-            if (half * WH + 4 * j4 < KP && v0ok)
-              *reinterpret_cast<float4*>(xas + c0 * LD + l * KP + half * WH + 4 * j4) =
-                  make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
+          for (int i = 0; i < NTW; ++i) {
+            const int w = i * 8 + 2 * ft;
+            if (w < KP) {
+              if (m0 + fg < Cin)
+                *reinterpret_cast<float2*>(xas + (m0 + fg) * LD + l * KP + w) = make_float2(acc[i][0], acc[i][1]);
+              if (m0 + fg + 8 < Cin)
+                *reinterpret_cast<float2*>(xas + (m0 + fg + 8) * LD + l * KP + w) = make_float2(acc[i][2], acc[i][3]);
+            }
           }
         }
-        if (chalf == 0 && lane < WH && half * WH + lane < KP) {   // ones row: column sums of xmu (0 on padded columns)
-          float sres = 0.f;
-          for (int v = 0; v < K; ++v) sres += xm_l[v * KP2 + lane];
-          xas[Cin * LD + l * KP + half * WH + lane] = sres;
+        // ones row: column sums of xmu (0 on padded columns); warp = frame, lane = w
+        for (int l = warp; l < pv; l += AMB_NT / 32) {
+          const float* xm_l = xms + ((b * PCH + l) * K) * KP2;
+          for (int w = lane; w < KP; w += 32) {
+            float sres = 0.f;
+            for (int v = 0; v < K; ++v) sres += xm_l[v * KP2 + w];
+            xas[Cin * LD + l * KP + w] = sres;
+          }
         }
       }
       // frames beyond pv: xa must read as zero in (c)
@@ -302,84 +314,93 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       }
 
       PH(4);
-      // ================= (d) gx += gxa_b xmu_b^T    (warp = (frame, v half, channel half), lane = channel)
-      for (int it = warp; it < 4 * pv; it += AMB_NT / 32) {
-        const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
-        const float* xmT_l = xmT + ((b * PCH + l) * K) * KP2 + half * WH;
-        for (int cg = 0; cg < Cin; cg += 64) {
-          const int c0 = cg + chalf * 32 + lane;
-          const bool v0ok = c0 < Cin;
-          float g0[KP];
+      // ================= (d) gx += gxa_b xmu_b^T on mma.sync: gx[c][l,v] += sum_w gxa[c][l,w] xmu_b[l][v][w]
+      {
+        constexpr int NTW = KP2 / 8;
+        const int MTc = (Cin + 15) >> 4;
+        for (int grp = warp; grp < pv * MTc; grp += AMB_NT / 32) {
+          const int l = grp / MTc, m0 = (grp % MTc) * 16;
+          float acc[NTW][4];
 #pragma unroll
-          for (int i = 0; i < KP / 4; ++i) {
-            const float4 t0 = *reinterpret_cast<const float4*>(gxas + (v0ok ? c0 : 0) * LD + l * KP + 4 * i);
-            g0[4 * i] = t0.x; g0[4 * i + 1] = t0.y; g0[4 * i + 2] = t0.z; g0[4 * i + 3] = t0.w;
-          }
-          float a0[WH];
+          for (int i = 0; i < NTW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+          const float* ar = gxas + (m0 + fg) * LD + l * KP + ft;
+          const float* br = xmT + ((b * PCH + l) * K + ft) * KP2 + fg;
+          for (int k0 = 0; k0 < K; k0 += 8) {
+            const bool k_lo = k0 + ft < K, k_hi = k0 + ft + 4 < K;
+            uint32_t ah[4], al[4];
+            split3(k_lo ? ar[k0] : 0.f, ah[0], al[0]);
+            split3(k_lo ? ar[k0 + 8 * LD] : 0.f, ah[1], al[1]);
+            split3(k_hi ? ar[k0 + 4] : 0.f, ah[2], al[2]);
+            split3(k_hi ? ar[k0 + 8 * LD + 4] : 0.f, ah[3], al[3]);
 #pragma unroll
-          for (int j = 0; j < WH; ++j) a0[j] = 0.f;
-#pragma unroll
-          for (int w = 0; w < KP; ++w) {
-            if (w < K) {
-              const float4* r4 = reinterpret_cast<const float4*>(xmT_l + w * KP2);
-#pragma unroll
-              for (int j4 = 0; j4 < WH / 4; ++j4) {
-                const float4 m = r4[j4];
-                a0[j4 * 4 + 0] = fmaf(g0[w], m.x, a0[j4 * 4 + 0]);
-                a0[j4 * 4 + 1] = fmaf(g0[w], m.y, a0[j4 * 4 + 1]);
-                a0[j4 * 4 + 2] = fmaf(g0[w], m.z, a0[j4 * 4 + 2]);
-                a0[j4 * 4 + 3] = fmaf(g0[w], m.w, a0[j4 * 4 + 3]);
-              }
+            for (int i = 0; i < NTW; ++i) {
+              uint32_t bh[2], bl[2];
+              split3(k_lo ? br[k0 * KP2 + i * 8] : 0.f, bh[0], bl[0]);
+              split3(k_hi ? br[(k0 + 4) * KP2 + i * 8] : 0.f, bh[1], bl[1]);
+              mma_tf32(acc[i], ah, bh);
+              mma_tf32(acc[i], ah, bl);
+              mma_tf32(acc[i], al, bh);
             }
           }
 #pragma unroll
-          for (int j4 = 0; j4 < WH / 4; ++j4) {
-            if (half * WH + 4 * j4 < KP && v0ok) {
-              float4* d = reinterpret_cast<float4*>(gxs + c0 * LD + l * KP + half * WH + 4 * j4);
-              float4 t = make_float4(a0[4 * j4], a0[4 * j4 + 1], a0[4 * j4 + 2], a0[4 * j4 + 3]);
-              if (b > 0) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-              *d = t;
+          for (int i = 0; i < NTW; ++i) {
+            const int v = i * 8 + 2 * ft;
+            if (v < KP) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = m0 + fg + 8 * h;
+                if (c < Cin) {
+                  float2* dp = reinterpret_cast<float2*>(gxs + c * LD + l * KP + v);
+                  float2 tv = make_float2(acc[i][2 * h], acc[i][2 * h + 1]);
+                  if (b > 0) { const float2 o = *dp; tv.x += o.x; tv.y += o.y; }
+                  *dp = tv;
+                }
+              }
             }
           }
         }
       }
 
       PH(5);
-      // ================= (e) gxmu_b[l][v][w] = sum_{c<=Cin} xaug[c][l,v] gxa_b[c][l,w]   (4x4 tiles) -> HBM
+      // ================= (e) gxmu_b[l][v][w] = sum_{c<=Cin} xaug[c][l,v] gxa_b[c][l,w] on mma.sync -> HBM
+      //                   warp = (frame, 16-row tile of v, half of the w tiles); K = c (zero rows above Cin)
       {
-        constexpr int NT4 = KP / 4;
-        const int ntile = pv * NT4 * NT4;
-        for (int tile = tid; tile < ntile; tile += AMB_NT) {
-          const int wt = tile % NT4;
-          int t = tile / NT4;
-          const int vt = t % NT4, l = t / NT4;
-          float acc[4][4];
+        constexpr int NTW = KP2 / 8, NH = (NTW + 1) / 2;
+        const int MTv = (K + 15) >> 4;
+        for (int grp = warp; grp < pv * MTv * 2; grp += AMB_NT / 32) {
+          const int nh = grp & 1, l = (grp >> 1) / MTv, m0 = ((grp >> 1) % MTv) * 16;
+          float acc[NH][4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < NH; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+          const float* ar = xs + ft * LD + l * KP + m0 + fg;
+          const float* br = gxas + ft * LD + l * KP + nh * NH * 8 + fg;
+          for (int k0 = 0; k0 < C1R8; k0 += 8) {
+            uint32_t ah[4], al[4];
+            split3(ar[k0 * LD], ah[0], al[0]);
+            split3(ar[k0 * LD + 8], ah[1], al[1]);
+            split3(ar[(k0 + 4) * LD], ah[2], al[2]);
+            split3(ar[(k0 + 4) * LD + 8], ah[3], al[3]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-          const float* xp = xs + l * KP + 4 * vt;
-          const float* gp = gxas + l * KP + 4 * wt;
-#pragma unroll 4
-          for (int c = 0; c < C1; ++c) {
-            const float4 xv = *reinterpret_cast<const float4*>(xp + c * LD);
-            const float4 gv = *reinterpret_cast<const float4*>(gp + c * LD);
-            const float xa_[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float ga_[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa_[i], ga_[j], acc[i][j]);
+            for (int i = 0; i < NH; ++i) {
+              uint32_t bh[2], bl[2];
+              split3(br[k0 * LD + i * 8], bh[0], bl[0]);
+              split3(br[(k0 + 4) * LD + i * 8], bh[1], bl[1]);
+              mma_tf32(acc[i], ah, bh);
+              mma_tf32(acc[i], ah, bl);
+              mma_tf32(acc[i], al, bh);
+            }
           }
           float* dst = q.gxm + ((long long)(n * nb + b) * P + p0 + l) * KK;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int v = 4 * vt + i;
-            if (v >= K) continue;
+          for (int i = 0; i < NH; ++i) {
+            const int w = (nh * NH + i) * 8 + 2 * ft;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int w = 4 * wt + j;
-              if (w < K) dst[q.adj_t ? (w * K + v) : (v * K + w)] = acc[i][j];
+            for (int h = 0; h < 2; ++h) {
+              const int v = m0 + fg + 8 * h;
+              if (v < K) {
+                if (w < K) dst[q.adj_t ? (w * K + v) : (v * K + w)] = acc[i][2 * h];
+                if (w + 1 < K) dst[q.adj_t ? ((w + 1) * K + v) : (v * K + w + 1)] = acc[i][2 * h + 1];
+              }
             }
           }
         }
@@ -451,7 +472,8 @@ static bool aggmix_bwd_geom(int Cin, int Cout, int P, int K, int nb, AggMixBwdGe
     const int npad = pch * g.KP;
     int ld = npad + 4;
     if ((ld / 4) % 2 == 0) ld += 4;
-    size_t f = (size_t)(3 * C1 + CoutR16 + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * CoutR8 * g.WS +
+    const int C1R8 = (C1 + 7) / 8 * 8;
+    size_t f = (size_t)(2 * C1R8 + C1 + CoutR16 + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * CoutR8 * g.WS +
                (size_t)nb * Cout + (size_t)nb * K * K * (pch + 1) + 32;
     if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 512) {
       g.PCH = pch;
