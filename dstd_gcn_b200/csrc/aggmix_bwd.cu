@@ -22,7 +22,9 @@ namespace dstd {
 // mma.sync each delivered value feeds 64-128 MACs.  tcgen05 would need hi/lo operand images in shared memory that do
 // not fit next to the frame-chunk tiles.
 __device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  // hi = x truncated to TF32 (one full-rate LOP3; cvt.rna.tf32 runs on the quarter-rate conversion pipe and these
+  // kernels issue ~20 splits per k-step), lo = x - hi exactly; |lo| < 2^-10 |x|, so hi*hi + hi*lo + lo*hi is good to ~2^-20
+  hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

@@ -58,9 +58,8 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
 }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));   // round to nearest: |lo| <= 2^-11 |x|
-  hi = __uint_as_float(h);
+  // truncation split on the full-rate logic pipe (cvt.rna.tf32 is quarter rate): |lo| < 2^-10 |x|, x == hi + lo exactly
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
   lo = x - hi;
 }
 
