@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdstd_b200.so")
+LIB_PATH = os.environ.get("DSTD_B200_LIB") or os.path.join(_HERE, "csrc", "libdstd_b200.so")   # override: A/B builds
 
 MAX_BRANCH = 2
 FLAG_ADJ_T = 1

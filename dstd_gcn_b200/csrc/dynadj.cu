@@ -202,6 +202,13 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
   };
   if (total > 0) prefetch(0);
 
+  // optional per-phase cycle counters (-DDSTD_PHASE_TIMING, printed by CTA 0)
+#ifdef DSTD_PHASE_TIMING
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define DPH(i) do { __syncthreads(); long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define DPH(i) do {} while (0)
+#endif
   for (long long st = 0; st < total; ++st) {
     const int n = (int)blockIdx.x + (int)(st / nchunks) * (int)gridDim.x;
     const int ci = (int)(st % nchunks);
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
     __syncthreads();                       // chunk st landed; everyone is done with the other buffer and with Ds
     if (st + 1 < total) prefetch(st + 1);  // overlaps with the whole chunk below
 
+    DPH(0);
     // 2. rebuild D chunk (+ ones row for the bias gradient); galpha += gxm * pd on the way
     {
       const float* pdg = q.pd + nb_ * P * KK + e0;
@@ -246,6 +254,7 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
       }
     }
     __syncthreads();
+    DPH(1);
     // 3a. static-adjacency gradient: sum over p
     if (tid < EC) {
       float s = 0.f;
@@ -270,6 +279,7 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
         }
     }
     __syncthreads();
+    DPH(2);
     // 4. gS = alpha * (Wrm^T gXm) * (1 - D^2), written over D
     for (int tile = tid; tile < n_kt * n_et; tile += 256) {
       const int kt = tile / n_et, et = tile - kt * n_et;
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
       }
     }
     __syncthreads();
+    DPH(3);
     // 5. gm1[k,v] = sum_w gS (lanes 24.. : one local row each) ; gm2[k,w] = -sum_v gS (lanes 0..K-1, K <= 24;
     //    wider K: second pass)
     for (int k = ty; k < P2; k += 8) {
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
         gms[r * PK + qq * K + v0 + vl] += s;
       }
     }
+    DPH(4);
     if (ci == nchunks - 1) {                 // sample finished: its gm rows go out
       __syncthreads();
       float* gmg = q.gm + nb_ * 4 * PK;
@@ -331,6 +343,11 @@ __global__ void __launch_bounds__(256) dynadj_bwd_kernel(DynAdjBwdParams q, int 
     }
   }
 
+#ifdef DSTD_PHASE_TIMING
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+    printf("dynadj_bwd phases (cycles, CTA 0): wait/stage %lld rebuildD %lld gA+gWrm %lld gS %lld sums %lld\n", tph[0],
+           tph[1], tph[2], tph[3], tph[4]);
+#endif
   // per-split partials
   const long long sb = (long long)blockIdx.x * q.nb + b;
   float* pw = q.part_wrm + sb * P * (P2 + 1);
