@@ -57,6 +57,12 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
   return done != 0;
 }
 
+__device__ __forceinline__ void mma_tf32_sync(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   // truncation split on the full-rate logic pipe (cvt.rna.tf32 is quarter rate): |lo| < 2^-10 |x|, x == hi + lo exactly
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
@@ -189,50 +195,65 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
 
     // ---- 2. per branch: aggregation into the UMMA A tile, then the tensor-core channel mix
     for (int b = 0; b < nb; ++b) {
-      for (int it = warp; it < 4 * pv; it += TC_NT / 32) {   // item = (frame, w half, channel half); lane = channel
-        const int l = it >> 2, half = (it >> 1) & 1, chalf = it & 1;
-        const float* xm_l = xms + ((b * PCH + l) * K) * KP + half * WH;
-        for (int cg = 0; cg < Cin; cg += 64) {
-          const int c0 = cg + chalf * 32 + lane;
-          const float* x0p = xs + min(c0, Cin - 1) * XS_LD + l * K;
-          float a0[WH];
+      // aggregation xa[c][l,w] = sum_v x[c][l,v] xm_b[l][v][w] on mma.sync (3xTF32, register fragments), written
+      // straight into the UMMA A tile (hi / lo).  warp = (frame, 16-channel tile), all w tiles; K = v masked at K
+      {
+        constexpr int NTW = KP / 8;
+        const int fg = lane >> 2, ft = lane & 3;
+        const int MTc = (Cin + 15) >> 4;
+        for (int grp = warp; grp < pv * MTc; grp += TC_NT / 32) {
+          const int l = grp / MTc, m0 = (grp % MTc) * 16;
+          float acc[NTW][4];
 #pragma unroll
-          for (int j = 0; j < WH; ++j) a0[j] = 0.f;
-#pragma unroll 2
-          for (int v = 0; v < K; ++v) {
-            const float x0 = x0p[v];
-            const float4* r4 = reinterpret_cast<const float4*>(xm_l + v * KP);
+          for (int i = 0; i < NTW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+          const float* ar = xs + min(m0 + fg, Cin - 1) * XS_LD + l * K + ft;
+          const float* ar8 = xs + min(m0 + fg + 8, Cin - 1) * XS_LD + l * K + ft;
+          const float* br = xms + ((b * PCH + l) * K + ft) * KP + fg;
+          for (int k0 = 0; k0 < K; k0 += 8) {
+            const bool k_lo = k0 + ft < K, k_hi = k0 + ft + 4 < K;
+            uint32_t ah[4], al[4];
+            float h_, l_;
+            split_tf32(k_lo ? ar[k0] : 0.f, h_, l_);       ah[0] = __float_as_uint(h_); al[0] = __float_as_uint(l_);
+            split_tf32(k_lo ? ar8[k0] : 0.f, h_, l_);      ah[1] = __float_as_uint(h_); al[1] = __float_as_uint(l_);
+            split_tf32(k_hi ? ar[k0 + 4] : 0.f, h_, l_);   ah[2] = __float_as_uint(h_); al[2] = __float_as_uint(l_);
+            split_tf32(k_hi ? ar8[k0 + 4] : 0.f, h_, l_);  ah[3] = __float_as_uint(h_); al[3] = __float_as_uint(l_);
 #pragma unroll
-            for (int j4 = 0; j4 < WH / 4; ++j4) {
-              const float4 m = r4[j4];
-              a0[j4 * 4 + 0] = fmaf(x0, m.x, a0[j4 * 4 + 0]);
-              a0[j4 * 4 + 1] = fmaf(x0, m.y, a0[j4 * 4 + 1]);
-              a0[j4 * 4 + 2] = fmaf(x0, m.z, a0[j4 * 4 + 2]);
-              a0[j4 * 4 + 3] = fmaf(x0, m.w, a0[j4 * 4 + 3]);
+            for (int i = 0; i < NTW; ++i) {
+              uint32_t bh[2], bl[2];
+              split_tf32(k_lo ? br[k0 * KP + i * 8] : 0.f, h_, l_);        bh[0] = __float_as_uint(h_); bl[0] = __float_as_uint(l_);
+              split_tf32(k_hi ? br[(k0 + 4) * KP + i * 8] : 0.f, h_, l_);  bh[1] = __float_as_uint(h_); bl[1] = __float_as_uint(l_);
+              mma_tf32_sync(acc[i], ah, bh);
+              mma_tf32_sync(acc[i], ah, bl);
+              mma_tf32_sync(acc[i], al, bh);
             }
           }
-          if (c0 < Cin) {
 #pragma unroll
-            for (int j = 0; j < WH; ++j) {
-              const int w = half * WH + j;
-              if (w < K) {
+          for (int i = 0; i < NTW; ++i) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = m0 + fg + 8 * (e >> 1), w = i * 8 + 2 * ft + (e & 1);
+              if (c < Cin && w < K) {
                 float hi, lo;
-                split_tf32(a0[j], hi, lo);
-                const int o = tc_off(l * K + w, c0, sbo_f);
+                split_tf32(acc[i][e], hi, lo);
+                const int o = tc_off(l * K + w, c, sbo_f);
                 a_hi[o] = hi;
                 a_lo[o] = lo;
               }
             }
           }
         }
-        if (chalf == 0 && lane < WH && half * WH + lane < K) {   // ones row (K index Cin): column sums of xm carry the bias
-          float s = 0.f;
-          for (int v = 0; v < K; ++v) s += xm_l[v * KP + lane];
-          float hi, lo;
-          split_tf32(s, hi, lo);
-          const int o = tc_off(l * K + half * WH + lane, Cin, sbo_f);
-          a_hi[o] = hi;
-          a_lo[o] = lo;
+        // ones row (K index Cin): column sums of xm carry the conv_f bias; warp = frame, lane = w
+        for (int l = warp; l < pv; l += TC_NT / 32) {
+          const float* xm_l = xms + ((b * PCH + l) * K) * KP;
+          for (int w = lane; w < K; w += 32) {
+            float s = 0.f;
+            for (int v = 0; v < K; ++v) s += xm_l[v * KP + w];
+            float hi, lo;
+            split_tf32(s, hi, lo);
+            const int o = tc_off(l * K + w, Cin, sbo_f);
+            a_hi[o] = hi;
+            a_lo[o] = lo;
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
