@@ -8,6 +8,8 @@
 //   backward: per sample, (v,w)-row chunks of D are rebuilt in shared memory and used by two register-blocked
 //             contractions: gWrm += gXm * D^T (accumulated in registers across the whole batch split) and
 //             gD = Wrm^T gXm -> gS = gD (1 - D^2) -> row/column sums give gm1 / gm2.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace dstd {
@@ -86,6 +88,118 @@ __global__ void __launch_bounds__(256) dynadj_fwd_kernel(DynAdjFwdParams q) {
   }
 }
 
+// ---- tensor-path forward: pd[p][e] = sum_k Wrm[p][k] D[k][e] + brm[p] as mma.sync m16n8k8 TF32 (3xTF32) with the
+// B fragments (the pairwise tanh values) COMPUTED IN REGISTERS in fragment layout: every D element is evaluated by
+// exactly one lane, never stored, and feeds all 16-row tiles of p; the A fragments (Wrm) come from shared memory.
+// The CUDA-core version above is limited by the shared-memory return path (one broadcast weight delivery per FMA).
+__device__ __forceinline__ void fsplit3(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void fmma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256) dynadj_fwd_mma_kernel(DynAdjFwdParams q, int WS) {
+  extern __shared__ __align__(16) float smem[];
+  const int P = q.P, K = q.K, PK = P * K, KK = K * K, P2 = 2 * P;
+  float* ms = smem;                        // [4][PK]
+  float* wsm = ms + ((4 * PK + 3) & ~3);   // [MT*16][WS]  Wrm, zero beyond P rows / 2P columns
+  float* bs = wsm + MT * 16 * WS;          // [MT*16]
+  const int n = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fg = lane >> 2, ft = lane & 3;
+  const float* mg = q.m + ((long long)(n * q.nb + b) * 4) * PK;
+  const float* wrm = q.w_rm[b];
+  float* pdg = q.pd + (long long)(n * q.nb + b) * P * KK;
+  for (int i = tid; i < 4 * PK; i += 256) ms[i] = __ldg(mg + i);
+  for (int i = tid; i < MT * 16 * WS; i += 256) {
+    const int p = i / WS, k = i - p * WS;
+    wsm[i] = (p < P && k < P2) ? __ldg(wrm + (long long)p * P2 + k) : 0.f;
+  }
+  for (int i = tid; i < MT * 16; i += 256) bs[i] = i < P ? __ldg(q.b_rm[b] + i) : 0.f;
+  __syncthreads();
+
+  const int NT = (KK + 7) >> 3, ntask = (NT + 1) >> 1;
+  const int ksteps = (P2 + 7) >> 3;
+  for (int task = warp; task < ntask; task += 8) {
+    int vi[2], wi[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = min((2 * task + i) * 8 + fg, KK - 1);
+      vi[i] = e / K;
+      wi[i] = e - vi[i] * K;
+    }
+    float acc[MT][2][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        acc[m][i][0] = acc[m][i][1] = bs[m * 16 + fg];
+        acc[m][i][2] = acc[m][i][3] = bs[m * 16 + fg + 8];
+      }
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int ka = ks * 8 + ft, kb = ka + 4;
+      uint32_t bh[2][2], bl[2][2];
+      {
+        const int ra = ka >= P ? 1 : 0, rb = kb >= P ? 1 : 0;
+        const float* m1a = ms + ra * PK + (ka - ra * P) * K;
+        const float* m1b = ms + rb * PK + (kb - rb * P) * K;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float da = ka < P2 ? fast_tanh(m1a[vi[i]] - m1a[2 * PK + wi[i]]) : 0.f;
+          const float db = kb < P2 ? fast_tanh(m1b[vi[i]] - m1b[2 * PK + wi[i]]) : 0.f;
+          fsplit3(da, bh[i][0], bl[i][0]);
+          fsplit3(db, bh[i][1], bl[i][1]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float* wr = wsm + (m * 16 + fg) * WS + ks * 8 + ft;
+        uint32_t ah[4], al[4];
+        fsplit3(wr[0], ah[0], al[0]);
+        fsplit3(wr[8 * WS], ah[1], al[1]);
+        fsplit3(wr[4], ah[2], al[2]);
+        fsplit3(wr[8 * WS + 4], ah[3], al[3]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          fmma_tf32(acc[m][i], ah, bh[i]);
+          fmma_tf32(acc[m][i], ah, bl[i]);
+          fmma_tf32(acc[m][i], al, bh[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = (2 * task + i) * 8 + 2 * ft;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = m * 16 + fg + 8 * h;
+          if (p < P) {
+            if (e < KK) pdg[(long long)p * KK + e] = acc[m][i][2 * h];
+            if (e + 1 < KK) pdg[(long long)p * KK + e + 1] = acc[m][i][2 * h + 1];
+          }
+        }
+      }
+  }
+}
+
+template <int MT>
+static int dynadj_fwd_mma_launch(const DynAdjFwdParams& q, cudaStream_t st) {
+  int WS = (2 * q.P + 7) / 8 * 8;
+  while ((WS / 4) % 2 == 0) WS += 4;          // WS/4 odd: conflict-free A-fragment loads
+  const size_t smem = ((size_t)((4 * q.P * q.K + 3) & ~3) + (size_t)MT * 16 * WS + MT * 16) * sizeof(float);
+  auto kern = dynadj_fwd_mma_kernel<MT>;
+  if (smem > 48 * 1024) ensure_max_smem((const void*)kern);
+  kern<<<dim3(q.N, q.nb), 256, smem, st>>>(q, WS);
+  count_launch();
+  return check_launch("dynadj_fwd_mma");
+}
+
 template <int RT>
 static int dynadj_fwd_launch(const DynAdjFwdParams& q, cudaStream_t st) {
   constexpr int NP = 2;
@@ -106,6 +220,12 @@ static int dynadj_fwd_launch(const DynAdjFwdParams& q, cudaStream_t st) {
 }
 
 int launch_dynadj_fwd(const DynAdjFwdParams& q, cudaStream_t st) {
+  static const bool simt = getenv("DSTD_DYNADJ_FWD_SIMT") != nullptr;   // A/B switch: CUDA-core version
+  if (!simt) {
+    if (q.P <= 16) return dynadj_fwd_mma_launch<1>(q, st);
+    if (q.P <= 32) return dynadj_fwd_mma_launch<2>(q, st);
+    if (q.P <= 48) return dynadj_fwd_mma_launch<3>(q, st);
+  }
   if (q.P <= 24) return dynadj_fwd_launch<24>(q, st);
   if (q.P <= 28) return dynadj_fwd_launch<28>(q, st);
   if (q.P <= 36) return dynadj_fwd_launch<36>(q, st);
