@@ -29,12 +29,31 @@ int check_launch(const char* what) {
   return DSTD_OK;
 }
 
+// the 227 KB per-CTA limit covers static + dynamic shared memory
+static int max_dyn_for(const void* kernel) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return MAX_DYN_SMEM;
+  return MAX_DYN_SMEM - (int)fa.sharedSizeBytes;
+}
+
 void ensure_max_smem(const void* kernel) {
   static std::mutex mu;
   static std::set<const void*> done;
   std::lock_guard<std::mutex> lk(mu);
   if (done.count(kernel)) return;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_for(kernel));
+  done.insert(kernel);
+}
+
+// Streaming kernels with modest dynamic shared memory: without a preference the driver picks the smallest carve-out
+// that fits ONE CTA (measured: bn_bwd_apply ran 1 CTA/SM), so ask for the largest shared-memory partition once.
+void prefer_smem_carveout(const void* kernel, bool need_max) {
+  static std::mutex mu;
+  static std::set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(kernel)) return;
+  if (need_max) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_for(kernel));
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   done.insert(kernel);
 }
 

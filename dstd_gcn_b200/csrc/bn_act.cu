@@ -18,16 +18,31 @@ namespace dstd {
 constexpr int BN_THREADS_MAX = 512;
 constexpr int BN_MAXJ = 8;       // positions per thread  -> T*V <= 4096
 // samples in flight per thread (memory-level parallelism): 8 for the dataset shapes (T*V <= 1024), 4 beyond
-#define BN_U 4
-#define BN_UB ((NJ) <= 1 ? 8 : 4)
-static int bn_u(int nj) { (void)nj; return 4; }
-static int bn_ub(int nj) { return nj <= 1 ? 8 : 4; }
+static int bn_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// samples per pipeline stage: the largest of 4/2/1 not above `cap` whose `planes_per_u` staged planes fit `budget`
+static int bn_pick_u(size_t plane_bytes, int planes_per_u, int cap, size_t budget) {
+  int u = 4;
+  while (u > 1 && (u > cap || (size_t)u * planes_per_u * plane_bytes > budget)) u >>= 1;
+  return u;
+}
+static int bn_u_cap() {        // forward apply
+  static const int u = bn_env("DSTD_BN_U", 4);
+  return u;
+}
+static int bn_ub_cap() {       // backward kernels
+  static const int u = bn_env("DSTD_BN_UB", 4);
+  return u;
+}
+static const size_t BN_SMEM_BUDGET = 100 * 1024;   // two CTAs per SM
 
 int bn_act_splits(int N, int C) {
   (void)C;
   static const int per_cta = [] {
     const char* e = getenv("DSTD_BN_SAMPLES_PER_CTA");     // tuning knob; default measured best on B200
-    int v = e ? atoi(e) : 8;
+    int v = e ? atoi(e) : 16;
     return v < 1 ? 1 : v;
   }();
   int s = (N + per_cta - 1) / per_cta;
@@ -78,72 +93,194 @@ struct BnFwdP {
   float* part;   // [S][C][V][2]
 };
 
-// stage BN_U planes of `src` (walked in its own memory order, coalesced) into sh[u][t*V+v]
-template <int NJ, int U>
-__device__ __forceinline__ void stage_planes(const View4& src, int c, int n, int n1, int T, int V, float* sh, int TV) {
-  float tmp[U][NJ];
-  int idx[NJ];
+// Per-thread position table, built once per CTA: the integer divisions of decode_pos and the 64-bit stride products
+// stay out of the per-sample loop (they were most of the instruction stream: 112 warp instructions per 32 elements
+// in bn_apply before, profiles/r01_ncu_full_bn_before.md).  Positions are enumerated in the memory order of `order`
+// (so that a warp's accesses to it are one contiguous sweep) and addressed in `addr`.
+template <int NJ>
+struct PosTab {
+  const float* base;    // addr.p + n0*sn + c*sc (uniform over the CTA)
+  int off[NJ];          // in-plane element offset of this thread's i-th position in `addr` (a plane spans < 2^31)
+  int idx[NJ];          // logical slot t*V+v, -1 = no position
+  int v[NJ];
+};
+template <int NJ>
+__device__ __forceinline__ void tab_init(PosTab<NJ>& tb, const View4& order, const View4& addr, int c, int n0, int T,
+                                         int V, int TV) {
+  tb.base = addr.p + (long long)n0 * addr.sn + (long long)c * addr.sc;
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     const int j = threadIdx.x + i * blockDim.x;
-    idx[i] = -1;
+    tb.idx[i] = -1;
+    tb.v[i] = 0;
+    tb.off[i] = 0;
     if (j < TV) {
       int t, v;
-      decode_pos(src, j, T, V, t, v);
-      idx[i] = t * V + v;
-      const float* p = src.p + (long long)n * src.sn + (long long)c * src.sc + pos_off(src, t, v);
-#pragma unroll
-      for (int u = 0; u < U; ++u) tmp[u][i] = (n + u < n1) ? __ldg(p + (long long)u * src.sn) : 0.f;
+      decode_pos(order, j, T, V, t, v);
+      tb.idx[i] = t * V + v;
+      tb.v[i] = v;
+      tb.off[i] = (int)pos_off(addr, t, v);
     }
   }
+}
+// ---- the three streaming kernels (apply, backward reduce, backward apply).
+// Inputs are staged into shared memory as LINEAR copies of each tensor's [T x V] plane in that tensor's own memory
+// order (8-byte cp.async when the plane is dense and 8-byte aligned: one instruction per two elements), double
+// buffered; the consumer, which walks positions in the OUTPUT's memory order, picks its element at the slot the
+// tensor's order implies (v*T+t or t*V+v), so a layout switch costs a strided shared-memory read and nothing else.
+// A thread keeps per owned position only the packed logical (t, v) under the two enumeration orders; addresses and
+// slots are re-derived with a few integer ops per U samples.  (Per-tensor offset tables in registers pushed these
+// kernels past 100 registers, and capped at 64 the compiler rematerialised whole address chains per element:
+// profiles/r01_ncu_full_bn_before.md.)
+template <int NJ>
+struct Pos2 {
+  int tf[NJ], vf[NJ];   // (t << 8) | v of position j = tid + i*blockDim in the T-fastest / V-fastest enumeration; -1 none
+};
+template <int NJ>
+__device__ __forceinline__ void pos_init(Pos2<NJ>& ps, int T, int V, int TV) {
 #pragma unroll
-  for (int i = 0; i < NJ; ++i)
-    if (idx[i] >= 0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) sh[u * TV + idx[i]] = tmp[u][i];
+  for (int i = 0; i < NJ; ++i) {
+    const int j = threadIdx.x + i * blockDim.x;
+    ps.tf[i] = ps.vf[i] = -1;
+    if (j < TV) {
+      int a = j / T;                 // T fastest: j = v*T + t
+      ps.tf[i] = ((j - a * T) << 8) | a;
+      a = j / V;                     // V fastest: j = t*V + v
+      ps.vf[i] = (a << 8) | (j - a * V);
     }
+  }
+}
+__device__ __forceinline__ void cp_async4_s(unsigned sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_s(unsigned sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+// how a [T x V] plane of `w` can be copied: 2 = dense and every plane 8-byte aligned, 1 = dense, 0 = generic strides
+__device__ __forceinline__ int plane_mode(const View4& w, int T, int V) {
+  const bool dense = t_fastest(w) ? (w.sp == 1 && w.sk == T) : (w.sk == 1 && w.sp == V);
+  if (!dense) return 0;
+  const bool al8 = ((reinterpret_cast<unsigned long long>(w.p) & 7ull) == 0) && !((w.sn | w.sc) & 1ll) && !((T * V) & 1);
+  return al8 ? 2 : 1;
+}
+// slot of logical (t, v) in a plane staged in w's memory order
+__device__ __forceinline__ int slot_of(bool tfast, int t, int v, int T, int V) { return tfast ? v * T + t : t * V + v; }
+
+// cp.async samples n .. n+U-1 (`left` of them exist) of channel plane c of `w` into the [U][T*V] region at shared
+// address `sdst`, each plane in w's own memory order
+template <int NJ, int U, bool FULL>
+__device__ __forceinline__ void stage_async(const Pos2<NJ>& ps, const View4& w, int c, int n, int left, unsigned sdst,
+                                            int T, int V) {
+  const int TV = T * V, mode = plane_mode(w, T, V);
+  const float* base = w.p + (long long)n * w.sn + (long long)c * w.sc;
+  if (mode == 2) {
+    for (int j = 2 * threadIdx.x; j < TV; j += 2 * blockDim.x) {
+      const float* p = base + j;
+      unsigned d = sdst + (unsigned)j * 4u;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) cp_async8_s(d, p);
+        p += w.sn;
+        d += (unsigned)TV * 4u;
+      }
+    }
+  } else {
+    const bool tfast = t_fastest(w);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int pk = tfast ? ps.tf[i] : ps.vf[i];
+      if (pk >= 0) {
+        const int j = threadIdx.x + i * blockDim.x;
+        const float* p = base + (mode ? (long long)j : (long long)(pk >> 8) * w.sp + (long long)(pk & 255) * w.sk);
+        unsigned d = sdst + (unsigned)j * 4u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (FULL || u < left) cp_async4_s(d, p);
+          p += w.sn;
+          d += (unsigned)TV * 4u;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ forward: statistics
 template <int NJ>
 __global__ void __launch_bounds__(BN_THREADS_MAX) bn_stats_kernel(BnFwdP q) {
   extern __shared__ float sh[];   // [2][T*V]
+  constexpr int SU = 8;
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
-  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
-  float a1[NJ], a2[NJ];
-  int idx[NJ];
+  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S), cnt = n1 - n0;
+  const long long sn = q.y.sn;
+  if (plane_mode(q.y, T, V) == 2) {
+    // dense, 8-byte aligned planes: two adjacent positions per thread, LDG.64, SU samples in flight
+    const bool tfast = t_fastest(q.y);
+    const float* base = q.y.p + (long long)n0 * sn + (long long)c * q.y.sc;
+    for (int j = 2 * threadIdx.x; j < TV; j += 2 * blockDim.x) {
+      int t0, v0, t1, v1;
+      decode_pos(q.y, j, T, V, t0, v0);
+      decode_pos(q.y, j + 1, T, V, t1, v1);
+      const float* sp0 = q.y.p + (long long)c * q.y.sc;   // shift = y[0, c, 0, v]
+      const float sh0 = __ldg(sp0 + (tfast ? (long long)v0 * T : (long long)v0));
+      const float sh1 = __ldg(sp0 + (tfast ? (long long)v1 * T : (long long)v1));
+      float a1x = 0.f, a2x = 0.f, a1y = 0.f, a2y = 0.f;
+      const float* p = base + j;
+      for (int nn = 0; nn < cnt; nn += SU) {
+        const int left = cnt - nn;
+        float2 d[SU];
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    a1[i] = a2[i] = 0.f;
-    idx[i] = -1;
-    const int j = threadIdx.x + i * blockDim.x;
-    if (j < TV) {
-      int t, v;
-      decode_pos(q.y, j, T, V, t, v);
-      idx[i] = t * V + v;
-      const float shift = __ldg(q.y.p + vix(q.y, 0, c, 0, v));
-      const float* p = q.y.p + (long long)c * q.y.sc + pos_off(q.y, t, v);
-      float s1 = 0.f, s2 = 0.f;
-      for (int n = n0; n < n1; n += BN_U) {
-        float d[BN_U];
+        for (int u = 0; u < SU; ++u) {
+          d[u] = (u < left) ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(sh0, sh1);
+          p += sn;
+        }
 #pragma unroll
-        for (int u = 0; u < BN_U; ++u) d[u] = (n + u < n1) ? __ldg(p + (long long)(n + u) * q.y.sn) - shift : 0.f;
-#pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
-          s1 += d[u];
-          s2 = fmaf(d[u], d[u], s2);
+        for (int u = 0; u < SU; ++u) {
+          const float dx = d[u].x - sh0, dy = d[u].y - sh1;
+          a1x += dx;
+          a2x = fmaf(dx, dx, a2x);
+          a1y += dy;
+          a2y = fmaf(dy, dy, a2y);
         }
       }
-      a1[i] = s1;
-      a2[i] = s2;
+      sh[t0 * V + v0] = a1x;
+      sh[TV + t0 * V + v0] = a2x;
+      sh[t1 * V + v1] = a1y;
+      sh[TV + t1 * V + v1] = a2y;
     }
-  }
+  } else {
+    PosTab<NJ> ty;
+    tab_init<NJ>(ty, q.y, q.y, c, n0, T, V, TV);
+    float a1[NJ], a2[NJ], shift[NJ];
 #pragma unroll
-  for (int i = 0; i < NJ; ++i)
-    if (idx[i] >= 0) {
-      sh[idx[i]] = a1[i];
-      sh[TV + idx[i]] = a2[i];
+    for (int i = 0; i < NJ; ++i) {
+      a1[i] = a2[i] = 0.f;
+      shift[i] = ty.idx[i] >= 0 ? __ldg(q.y.p + (long long)c * q.y.sc + (long long)ty.v[i] * q.y.sk) : 0.f;
     }
+    for (int nn = 0; nn < cnt; nn += SU) {
+      const int left = cnt - nn;
+      float d[NJ][SU];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const float* p = ty.base + (long long)nn * sn + ty.off[i];
+#pragma unroll
+        for (int u = 0; u < SU; ++u, p += sn) d[i][u] = (ty.idx[i] >= 0 && u < left) ? __ldg(p) - shift[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          a1[i] += d[i][u];
+          a2[i] = fmaf(d[i][u], d[i][u], a2[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i)
+      if (ty.idx[i] >= 0) {
+        sh[ty.idx[i]] = a1[i];
+        sh[TV + ty.idx[i]] = a2[i];
+      }
+  }
   __syncthreads();
   if (threadIdx.x < V) {
     int v = threadIdx.x;
@@ -158,30 +295,30 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_stats_kernel(BnFwdP q) {
   }
 }
 
-__global__ void bn_finalize_kernel(BnFwdP q) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0 && q.nbt) *q.nbt += 1;
-  if (idx >= q.C * q.V) return;
-  const int c = idx / q.V, v = idx - c * q.V;
-  double s1 = 0., s2 = 0.;
-  for (int s = 0; s < q.S; ++s) {
-    const float* p = q.part + (((long long)s * q.C + c) * q.V + v) * 2;
-    s1 += p[0];
-    s2 += p[1];
-  }
-  const double cnt = (double)q.N * q.T;
-  const double shift = __ldg(q.y.p + vix(q.y, 0, c, 0, v));
-  const double dm = s1 / cnt;
-  double var = s2 / cnt - dm * dm;
-  if (var < 0.) var = 0.;
-  const double mean = shift + dm;
-  const int pi = bn_pidx(c, v, q.C, q.V, q.vc_order);
-  q.save_mean[pi] = (float)mean;
-  q.save_invstd[pi] = (float)(1.0 / sqrt(var + (double)q.eps));
-  if (q.running_mean) {
-    const double unb = cnt > 1. ? var * cnt / (cnt - 1.) : var;
-    q.running_mean[pi] = (float)((1.0 - q.momentum) * q.running_mean[pi] + q.momentum * mean);
-    q.running_var[pi] = (float)((1.0 - q.momentum) * q.running_var[pi] + q.momentum * unb);
+// Sum the per-split partial pairs of channel c for every v, in a fixed order (so that every CTA of the channel gets
+// bit-identical totals): 8 lanes per v, strided over the splits, combined with a butterfly.  Called by all threads;
+// the totals land in tot[v][0..1].  This replaces a separate "finalize" launch between the reduction and the apply
+// pass (9 us each, 76 of them per training step).
+__device__ __forceinline__ void sum_partials(const float* part, int S, int C, int c, int V, double (*tot)[2]) {
+  const int lim = (V * 8 + 31) & ~31;
+  for (int idx = threadIdx.x; idx < lim; idx += blockDim.x) {
+    const int v = idx >> 3, k = idx & 7;
+    double s1 = 0., s2 = 0.;
+    if (v < V)
+      for (int ss = k; ss < S; ss += 8) {
+        const float* p = part + (((long long)ss * C + c) * V + v) * 2;
+        s1 += p[0];
+        s2 += p[1];
+      }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (k == 0 && v < V) {
+      tot[v][0] = s1;
+      tot[v][1] = s2;
+    }
   }
 }
 
@@ -193,64 +330,130 @@ __global__ void bn_eval_stats_kernel(BnFwdP q) {
 }
 
 // ------------------------------------------------------------------------------------------ forward: apply
-// positions are walked in the memory order of `out`; y / r kept in the other order go through shared memory.
-// BN_U samples are in flight per thread.
-template <int NJ>
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_apply_kernel(BnFwdP q) {
-  extern __shared__ float sh[];   // [2][BN_U][T*V] staging (y, r)
-  const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
-  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
-  const bool y_stage = !same_order(q.y, q.out);
-  const bool r_stage = q.r.p && !same_order(q.r, q.out);
-  const float slope = q.prelu ? __ldg(q.prelu) : 1.f;
-  float* shy = sh;
-  float* shr = sh + BN_U * TV;
-  int tt[NJ], vv[NJ];
-  float sc[NJ], sf[NJ], sm[NJ];   // out = (y - mean) * (gamma * invstd) + beta  (centred first: no cancellation)
+// Positions are walked in the memory order of `out`.  Consumer state hoisted out of the sample loop: per position the
+// running output pointer and the shared-memory slots of y and r.
+template <int NJ, int U, bool FULL, bool MASK>
+__device__ __forceinline__ void bn_apply_consume(const BnFwdP& q, const float* stage, float* (&op)[NJ],
+                                                 const int (&sy)[NJ], const int (&sr)[NJ], const int (&me)[NJ], int c,
+                                                 int n, int left, const float (&sm)[NJ], const float (&sc)[NJ],
+                                                 const float (&sf)[NJ], float slope, bool has_r) {
+  const int TV = q.T * q.V;
+  const long long osn = q.out.sn;
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    tt[i] = -1;
-    vv[i] = 0;
-    sc[i] = sf[i] = sm[i] = 0.f;
-    const int j = threadIdx.x + i * blockDim.x;
-    if (j < TV) {
-      decode_pos(q.out, j, T, V, tt[i], vv[i]);
-      const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-      const float g = __ldg(q.gamma + pi), is = q.save_invstd[pi];
-      sm[i] = q.save_mean[pi];
-      sc[i] = g * is;
-      sf[i] = __ldg(q.beta + pi);
+    if (sy[i] >= 0) {
+      const float* py = stage + sy[i];
+      const float* pr = stage + U * TV + sr[i];
+      float* o = op[i];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) {
+          float pre = fmaf(*py - sm[i], sc[i], sf[i]);
+          if (has_r) pre += *pr;
+          float a = pre > 0.f ? pre : slope * pre;
+          if (MASK) a *= __ldg(q.mask + ((long long)(n + u) * q.C + c) * TV + me[i]);
+          *o = a;
+        }
+        o += osn;
+        py += TV;
+        pr += TV;
+      }
+      op[i] = o;
     }
   }
-  for (int n = n0; n < n1; n += BN_U) {
-    if (y_stage || r_stage) {
-      __syncthreads();
-      if (y_stage) stage_planes<NJ, BN_U>(q.y, c, n, n1, T, V, shy, TV);
-      if (r_stage) stage_planes<NJ, BN_U>(q.r, c, n, n1, T, V, shr, TV);
-      __syncthreads();
+}
+
+template <int NJ, int U>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_apply_kernel(BnFwdP q) {
+  extern __shared__ float sh[];   // [2 stages][nst = 1 (y) or 2 (y, r)][U][T*V]
+  const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
+  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S), cnt = n1 - n0;
+  const bool has_r = q.r.p != nullptr;
+  const float slope = q.prelu ? __ldg(q.prelu) : 1.f;
+  const int stage_f = (has_r ? 2 : 1) * U * TV, iters = (cnt + U - 1) / U;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+  Pos2<NJ> ps;
+  pos_init<NJ>(ps, T, V, TV);
+  auto issue = [&](int it) {
+    const unsigned d = sbase + (unsigned)((it & 1) * stage_f) * 4u;
+    const int n = n0 + it * U, left = n1 - n;
+    if (left >= U) {
+      stage_async<NJ, U, true>(ps, q.y, c, n, left, d, T, V);
+      if (has_r) stage_async<NJ, U, true>(ps, q.r, c, n, left, d + (unsigned)(U * TV) * 4u, T, V);
+    } else {
+      stage_async<NJ, U, false>(ps, q.y, c, n, left, d, T, V);
+      if (has_r) stage_async<NJ, U, false>(ps, q.r, c, n, left, d + (unsigned)(U * TV) * 4u, T, V);
     }
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      if (tt[i] >= 0) {
-        const int t = tt[i], v = vv[i], e = t * V + v;
-        float yv[BN_U], rv[BN_U], mv[BN_U];
-#pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
-          const bool ok = n + u < n1;
-          yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
-          rv[u] = !q.r.p ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
-          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+  };
+  if (iters > 0) issue(0);
+  cp_async_commit();
+  __shared__ double tot[32][2];
+  __shared__ float st_mean[32], st_is[32];
+  if (q.training) {   // batch statistics from the split partials; the s == 0 CTA of the channel publishes them
+    sum_partials(q.part, q.S, q.C, c, V, tot);
+    __syncthreads();
+    if (threadIdx.x < V) {
+      const int v = threadIdx.x;
+      const double cntd = (double)q.N * q.T;
+      const double shift = __ldg(q.y.p + vix(q.y, 0, c, 0, v));
+      const double dm = tot[v][0] / cntd;
+      double var = tot[v][1] / cntd - dm * dm;
+      if (var < 0.) var = 0.;
+      const double mean = shift + dm;
+      const float fm = (float)mean, fi = (float)(1.0 / sqrt(var + (double)q.eps));
+      st_mean[v] = fm;
+      st_is[v] = fi;
+      if (s == 0) {
+        const int pi = bn_pidx(c, v, q.C, V, q.vc_order);
+        q.save_mean[pi] = fm;
+        q.save_invstd[pi] = fi;
+        if (q.running_mean) {
+          const double unb = cntd > 1. ? var * cntd / (cntd - 1.) : var;
+          q.running_mean[pi] = (float)((1.0 - q.momentum) * q.running_mean[pi] + q.momentum * mean);
+          q.running_var[pi] = (float)((1.0 - q.momentum) * q.running_var[pi] + q.momentum * unb);
         }
-#pragma unroll
-        for (int u = 0; u < BN_U; ++u) {
-          if (n + u < n1) {
-            const float pre = fmaf(yv[u] - sm[i], sc[i], sf[i]) + rv[u];
-            const float a = pre > 0.f ? pre : slope * pre;
-            q.out.p[vix(q.out, n + u, c, t, v)] = a * mv[u];
-          }
-        }
+        if (c == 0 && v == 0 && q.nbt) *q.nbt += 1;
       }
     }
+    __syncthreads();
+  }
+  float sc[NJ], sf[NJ], sm[NJ];   // out = (y - mean) * (gamma * invstd) + beta  (centred first: no cancellation)
+  float* op[NJ];
+  int sy[NJ], sr[NJ], me[NJ];
+  {
+    const bool tfast = t_fastest(q.out), tf_y = t_fastest(q.y), tf_r = has_r && t_fastest(q.r);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      sc[i] = sf[i] = sm[i] = 0.f;
+      op[i] = nullptr;
+      sy[i] = -1;
+      sr[i] = me[i] = 0;
+      const int pk = tfast ? ps.tf[i] : ps.vf[i];
+      if (pk >= 0) {
+        const int t = pk >> 8, v = pk & 255;
+        const int pi = bn_pidx(c, v, q.C, V, q.vc_order);
+        const float g = __ldg(q.gamma + pi), is = q.training ? st_is[v] : q.save_invstd[pi];
+        sm[i] = q.training ? st_mean[v] : q.save_mean[pi];
+        sc[i] = g * is;
+        sf[i] = __ldg(q.beta + pi);
+        op[i] = q.out.p + vix(q.out, n0, c, t, v);
+        sy[i] = slot_of(tf_y, t, v, T, V);
+        sr[i] = slot_of(tf_r, t, v, T, V);
+        me[i] = t * V + v;
+      }
+    }
+  }
+  for (int it = 0; it < iters; ++it) {
+    if (it + 1 < iters) issue(it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int n = n0 + it * U, left = n1 - n;
+    const float* stage = sh + (it & 1) * stage_f;
+    if (q.mask) bn_apply_consume<NJ, U, false, true>(q, stage, op, sy, sr, me, c, n, left, sm, sc, sf, slope, has_r);
+    else if (left >= U) bn_apply_consume<NJ, U, true, false>(q, stage, op, sy, sr, me, c, n, left, sm, sc, sf, slope, has_r);
+    else bn_apply_consume<NJ, U, false, false>(q, stage, op, sy, sr, me, c, n, left, sm, sc, sf, slope, has_r);
+    __syncthreads();   // the buffer is refilled by the prefetch of the next iteration
   }
 }
 
@@ -280,77 +483,119 @@ __device__ __forceinline__ float bn_gpre(bool has_prelu, float yv, float rv, flo
   return gv;
 }
 
-// pass 1: per-(c,v) sums of gpre and gpre*xhat, PReLU slope gradient.  Positions in gout's memory order.
-template <int NJ>
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q) {
-  extern __shared__ float sh[];   // [2][BN_UB][T*V]
-  __shared__ float red[32];
-  const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
-  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
-  const bool has_prelu = q.prelu != nullptr;
-  const bool use_r = q.r.p && has_prelu;
-  const bool y_stage = !same_order(q.y, q.gout);
-  const bool r_stage = use_r && !same_order(q.r, q.gout);
-  const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
-  float* shy = sh;
-  float* shr = sh + BN_UB * TV;
-  int tt[NJ], vv[NJ];
-  float mu[NJ], is[NJ], g[NJ], b[NJ], a1[NJ], a2[NJ];
-  float gsl = 0.f;
+// pass 1: per-(c,v) sums of gpre and gpre*xhat, PReLU slope gradient.  Positions in gout's memory order; gout, y
+// and r come through shared memory (cp.async, double-buffered) like in the forward.
+template <int NJ, int U, bool FULL, bool MASK>
+__device__ __forceinline__ void bn_bwd_reduce_consume(const BnBwdP& q, const float* stage, const int (&sg)[NJ],
+                                                      const int (&sy)[NJ], const int (&sr)[NJ], const int (&me)[NJ],
+                                                      int c, int n, int left, const float (&mu)[NJ],
+                                                      const float (&is)[NJ], const float (&g)[NJ],
+                                                      const float (&b)[NJ], float slope, bool has_prelu, bool use_r,
+                                                      float (&a1)[NJ], float (&a2)[NJ], float& gsl) {
+  const int TV = q.T * q.V;
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    tt[i] = -1;
-    vv[i] = 0;
-    mu[i] = is[i] = g[i] = b[i] = a1[i] = a2[i] = 0.f;
-    const int j = threadIdx.x + i * blockDim.x;
-    if (j < TV) {
-      decode_pos(q.gout, j, T, V, tt[i], vv[i]);
-      const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-      mu[i] = __ldg(q.save_mean + pi);
-      is[i] = __ldg(q.save_invstd + pi);
-      g[i] = __ldg(q.gamma + pi);
-      b[i] = __ldg(q.beta + pi);
-    }
-  }
-  for (int n = n0; n < n1; n += BN_UB) {
-    if (y_stage || r_stage) {
-      __syncthreads();
-      if (y_stage) stage_planes<NJ, BN_UB>(q.y, c, n, n1, T, V, shy, TV);
-      if (r_stage) stage_planes<NJ, BN_UB>(q.r, c, n, n1, T, V, shr, TV);
-      __syncthreads();
-    }
+    if (sg[i] >= 0) {
+      const float* pg = stage + sg[i];
+      const float* py = stage + U * TV + sy[i];
+      const float* pr = stage + 2 * U * TV + sr[i];
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      if (tt[i] >= 0) {
-        const int t = tt[i], v = vv[i], e = t * V + v;
-        float yv[BN_UB], rv[BN_UB], gv[BN_UB], mv[BN_UB];
-#pragma unroll
-        for (int u = 0; u < BN_UB; ++u) {
-          const bool ok = n + u < n1;
-          yv[u] = y_stage ? shy[u * TV + e] : (ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f);
-          rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
-          gv[u] = ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, t, v)) : 0.f;
-          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) {
+          const float rv = use_r ? *pr : 0.f;
+          const float mv = MASK ? __ldg(q.mask + ((long long)(n + u) * q.C + c) * TV + me[i]) : 1.f;
+          float xhat, gs;
+          const float gp = bn_gpre(has_prelu, *py, rv, *pg, mv, mu[i], is[i], g[i], b[i], slope, xhat, gs);
+          a1[i] += gp;
+          a2[i] = fmaf(gp, xhat, a2[i]);
+          gsl += gs;
         }
-#pragma unroll
-        for (int u = 0; u < BN_UB; ++u) {
-          if (n + u < n1) {
-            float xhat, gs;
-            const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
-            a1[i] += gp;
-            a2[i] = fmaf(gp, xhat, a2[i]);
-            gsl += gs;
-          }
-        }
+        pg += TV;
+        py += TV;
+        pr += TV;
       }
     }
   }
+}
+
+template <int NJ, int U>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_reduce_kernel(BnBwdP q) {
+  extern __shared__ float sh[];   // [2 stages][nst = 2 (gout, y) or 3 (+ r)][U][T*V]
+  __shared__ float red[32];
+  const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
+  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S), cnt = n1 - n0;
+  const bool has_prelu = q.prelu != nullptr;
+  const bool use_r = q.r.p && has_prelu;
+  const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
+  const int stage_f = (use_r ? 3 : 2) * U * TV, iters = (cnt + U - 1) / U;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+  Pos2<NJ> ps;
+  pos_init<NJ>(ps, T, V, TV);
+  auto issue = [&](int it) {
+    const unsigned d = sbase + (unsigned)((it & 1) * stage_f) * 4u, du = (unsigned)(U * TV) * 4u;
+    const int n = n0 + it * U, left = n1 - n;
+    if (left >= U) {
+      stage_async<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
+      stage_async<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
+    } else {
+      stage_async<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
+      stage_async<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
+    }
+  };
+  if (iters > 0) issue(0);
+  cp_async_commit();
+  float mu[NJ], is[NJ], g[NJ], b[NJ], a1[NJ], a2[NJ];
+  int sg[NJ], sy[NJ], sr[NJ], me[NJ];
+  float gsl = 0.f;
+  {
+    const bool tfast = t_fastest(q.gout), tf_y = t_fastest(q.y), tf_r = use_r && t_fastest(q.r);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      mu[i] = is[i] = g[i] = b[i] = a1[i] = a2[i] = 0.f;
+      sg[i] = -1;
+      sy[i] = sr[i] = me[i] = 0;
+      const int pk = tfast ? ps.tf[i] : ps.vf[i];
+      if (pk >= 0) {
+        const int t = pk >> 8, v = pk & 255;
+        const int pi = bn_pidx(c, v, q.C, V, q.vc_order);
+        mu[i] = __ldg(q.save_mean + pi);
+        is[i] = __ldg(q.save_invstd + pi);
+        g[i] = __ldg(q.gamma + pi);
+        b[i] = __ldg(q.beta + pi);
+        sg[i] = slot_of(tfast, t, v, T, V);
+        sy[i] = slot_of(tf_y, t, v, T, V);
+        sr[i] = slot_of(tf_r, t, v, T, V);
+        me[i] = t * V + v;
+      }
+    }
+  }
+  for (int it = 0; it < iters; ++it) {
+    if (it + 1 < iters) issue(it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int n = n0 + it * U, left = n1 - n;
+    const float* stage = sh + (it & 1) * stage_f;
+    if (q.mask)
+      bn_bwd_reduce_consume<NJ, U, false, true>(q, stage, sg, sy, sr, me, c, n, left, mu, is, g, b, slope, has_prelu,
+                                                use_r, a1, a2, gsl);
+    else if (left >= U)
+      bn_bwd_reduce_consume<NJ, U, true, false>(q, stage, sg, sy, sr, me, c, n, left, mu, is, g, b, slope, has_prelu,
+                                                use_r, a1, a2, gsl);
+    else
+      bn_bwd_reduce_consume<NJ, U, false, false>(q, stage, sg, sy, sr, me, c, n, left, mu, is, g, b, slope, has_prelu,
+                                                 use_r, a1, a2, gsl);
+    __syncthreads();
+  }
+  cp_async_wait<0>();
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    if (tt[i] >= 0) {
-      sh[tt[i] * V + vv[i]] = a1[i];
-      sh[TV + tt[i] * V + vv[i]] = a2[i];
+    if (sg[i] >= 0) {
+      sh[me[i]] = a1[i];
+      sh[TV + me[i]] = a2[i];
     }
   }
   __syncthreads();
@@ -369,125 +614,212 @@ __global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_reduce_kernel(BnBwdP q)
   if (threadIdx.x == 0) q.part_p[(long long)s * q.C + c] = tot;
 }
 
-__global__ void bn_bwd_finalize_kernel(BnBwdP q) {
-  __shared__ float red[32];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < q.C * q.V) {
-    const int c = idx / q.V, v = idx - c * q.V;
-    double s1 = 0., s2 = 0.;
-    for (int s = 0; s < q.S; ++s) {
-      const float* p = q.part + (((long long)s * q.C + c) * q.V + v) * 2;
-      s1 += p[0];
-      s2 += p[1];
+// pass 2: gy (and gr).  Positions in gy's memory order; y, gout and r come through shared memory (cp.async,
+// double-buffered), gr leaves through it.
+template <int NJ, int U, bool FULL, bool MASK>
+__device__ __forceinline__ void bn_bwd_apply_consume(const BnBwdP& q, const float* stage, float* sho, float* (&gyp)[NJ],
+                                                     const int (&sg)[NJ], const int (&sy)[NJ], const int (&sr)[NJ],
+                                                     const int (&so)[NJ], const int (&me)[NJ], int c, int n, int left,
+                                                     const float (&mu)[NJ], const float (&is)[NJ],
+                                                     const float (&g)[NJ], const float (&b)[NJ],
+                                                     const float (&gi)[NJ], const float (&k1)[NJ],
+                                                     const float (&k2)[NJ], float slope, bool has_prelu, bool use_r,
+                                                     bool has_gr) {
+  const int TV = q.T * q.V;
+  const long long gysn = q.gy.sn;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    if (sg[i] >= 0) {
+      const float* pg = stage + sg[i];
+      const float* py = stage + U * TV + sy[i];
+      const float* pr = stage + 2 * U * TV + sr[i];
+      float* po = sho + so[i];
+      float* o = gyp[i];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) {
+          const float rv = use_r ? *pr : 0.f;
+          const float mv = MASK ? __ldg(q.mask + ((long long)(n + u) * q.C + c) * TV + me[i]) : 1.f;
+          float xhat, gs;
+          const float gp = bn_gpre(has_prelu, *py, rv, *pg, mv, mu[i], is[i], g[i], b[i], slope, xhat, gs);
+          *o = gi[i] * (gp - k1[i] - xhat * k2[i]);
+          if (has_gr) *po = gp;
+        }
+        o += gysn;
+        pg += TV;
+        py += TV;
+        pr += TV;
+        po += TV;
+      }
+      gyp[i] = o;
     }
-    const int pi = bn_pidx(c, v, q.C, q.V, q.vc_order);
-    q.gbeta[pi] = (float)s1;
-    q.ggamma[pi] = (float)s2;
-  }
-  if (blockIdx.x == 0 && q.gprelu) {   // deterministic fixed-order sum of the slope partials
-    float a = 0.f;
-    for (int i = threadIdx.x; i < q.S * q.C; i += blockDim.x) a += q.part_p[i];
-    float tot = block_sum(a, red);
-    if (threadIdx.x == 0) q.gprelu[0] = tot;
   }
 }
 
-// pass 2: gy (and gr).  Positions in gy's memory order (= y's: gy is allocated like y).
-template <int NJ>
-__global__ void __launch_bounds__(BN_THREADS_MAX) bn_bwd_apply_kernel(BnBwdP q) {
-  extern __shared__ float sh[];   // [3][BN_UB][T*V]: gout, r staging; gr transposition
+template <int NJ, int U>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP q) {
+  extern __shared__ float sh[];   // [2 stages][nst = 2 (gout, y) or 3 (+ r)][U][T*V], then [U][T*V] for gr
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
-  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S);
+  const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S), cnt = n1 - n0;
   const bool has_prelu = q.prelu != nullptr;
   const bool use_r = q.r.p && has_prelu;
-  const bool g_stage = !same_order(q.gout, q.gy);
-  const bool r_stage = use_r && !same_order(q.r, q.gy);
-  const bool gr_stage = q.gr.p && !same_order(q.gr, q.gy);
+  const bool has_gr = q.gr.p != nullptr;
   const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
   const float icnt = 1.0f / ((float)q.N * (float)T);
-  float* shg = sh;
-  float* shr = sh + BN_UB * TV;
-  float* sho = sh + 2 * BN_UB * TV;
-  int tt[NJ], vv[NJ];
-  float mu[NJ], is[NJ], g[NJ], b[NJ], k1[NJ], k2[NJ];
+  const int stage_f = (use_r ? 3 : 2) * U * TV, iters = (cnt + U - 1) / U;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+  float* sho = sh + 2 * stage_f;                       // gr hand-over, each plane in gr's memory order
+  const int gr_mode = has_gr ? plane_mode(q.gr, T, V) : 0;
+  const bool tfast_gr = has_gr && t_fastest(q.gr);
+  Pos2<NJ> ps;
+  pos_init<NJ>(ps, T, V, TV);
+  auto issue = [&](int it) {
+    const unsigned d = sbase + (unsigned)((it & 1) * stage_f) * 4u, du = (unsigned)(U * TV) * 4u;
+    const int n = n0 + it * U, left = n1 - n;
+    if (left >= U) {
+      stage_async<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
+      stage_async<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
+    } else {
+      stage_async<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
+      stage_async<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
+    }
+  };
+  if (iters > 0) issue(0);
+  cp_async_commit();
+  // sums of pass 1 over the splits; the s == 0 CTA of the channel publishes the parameter gradients
+  __shared__ double tot[32][2];
+  __shared__ float red[32];
+  sum_partials(q.part, q.S, q.C, c, V, tot);
+  if (c == 0 && s == 0 && q.gprelu) {   // fixed-order sum of the slope partials
+    float a = 0.f;
+    for (int i = threadIdx.x; i < q.S * q.C; i += blockDim.x) a += q.part_p[i];
+    const float t = block_sum(a, red);
+    if (threadIdx.x == 0) q.gprelu[0] = t;
+  }
+  __syncthreads();
+  if (s == 0 && threadIdx.x < V) {
+    const int pi = bn_pidx(c, threadIdx.x, q.C, V, q.vc_order);
+    q.gbeta[pi] = (float)tot[threadIdx.x][0];
+    q.ggamma[pi] = (float)tot[threadIdx.x][1];
+  }
+  // per position: xhat = (y - mu) * is;  gy = gi * (gp - k1 - xhat * k2)
+  float mu[NJ], is[NJ], g[NJ], b[NJ], gi[NJ], k1[NJ], k2[NJ];
+  float* gyp[NJ];
+  int sg[NJ], sy[NJ], sr[NJ], so[NJ], me[NJ];
+  {
+    const bool tfast = t_fastest(q.gy), tf_g = t_fastest(q.gout), tf_y = t_fastest(q.y), tf_r = use_r && t_fastest(q.r);
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    tt[i] = -1;
-    vv[i] = 0;
-    mu[i] = is[i] = g[i] = b[i] = k1[i] = k2[i] = 0.f;
-    const int j = threadIdx.x + i * blockDim.x;
-    if (j < TV) {
-      decode_pos(q.gy, j, T, V, tt[i], vv[i]);
-      const int pi = bn_pidx(c, vv[i], q.C, V, q.vc_order);
-      mu[i] = __ldg(q.save_mean + pi);
-      is[i] = __ldg(q.save_invstd + pi);
-      g[i] = __ldg(q.gamma + pi);
-      b[i] = __ldg(q.beta + pi);
-      if (q.training) {
-        k1[i] = q.gbeta[pi] * icnt;
-        k2[i] = q.ggamma[pi] * icnt;
+    for (int i = 0; i < NJ; ++i) {
+      mu[i] = is[i] = g[i] = b[i] = gi[i] = k1[i] = k2[i] = 0.f;
+      gyp[i] = nullptr;
+      sg[i] = -1;
+      sy[i] = sr[i] = so[i] = me[i] = 0;
+      const int pk = tfast ? ps.tf[i] : ps.vf[i];
+      if (pk >= 0) {
+        const int t = pk >> 8, v = pk & 255;
+        const int pi = bn_pidx(c, v, q.C, V, q.vc_order);
+        mu[i] = __ldg(q.save_mean + pi);
+        is[i] = __ldg(q.save_invstd + pi);
+        g[i] = __ldg(q.gamma + pi);
+        b[i] = __ldg(q.beta + pi);
+        gi[i] = g[i] * is[i];
+        if (q.training) {
+          k1[i] = (float)tot[v][0] * icnt;
+          k2[i] = (float)tot[v][1] * icnt;
+        }
+        gyp[i] = q.gy.p + vix(q.gy, n0, c, t, v);
+        sg[i] = slot_of(tf_g, t, v, T, V);
+        sy[i] = slot_of(tf_y, t, v, T, V);
+        sr[i] = slot_of(tf_r, t, v, T, V);
+        so[i] = slot_of(tfast_gr, t, v, T, V);
+        me[i] = t * V + v;
       }
     }
   }
-  for (int n = n0; n < n1; n += BN_UB) {
-    if (g_stage || r_stage || gr_stage) {
+  for (int it = 0; it < iters; ++it) {
+    if (it + 1 < iters) issue(it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int n = n0 + it * U, left = n1 - n;
+    const float* stage = sh + (it & 1) * stage_f;
+    if (q.mask)
+      bn_bwd_apply_consume<NJ, U, false, true>(q, stage, sho, gyp, sg, sy, sr, so, me, c, n, left, mu, is, g, b, gi, k1,
+                                               k2, slope, has_prelu, use_r, has_gr);
+    else if (left >= U)
+      bn_bwd_apply_consume<NJ, U, true, false>(q, stage, sho, gyp, sg, sy, sr, so, me, c, n, left, mu, is, g, b, gi, k1,
+                                               k2, slope, has_prelu, use_r, has_gr);
+    else
+      bn_bwd_apply_consume<NJ, U, false, false>(q, stage, sho, gyp, sg, sy, sr, so, me, c, n, left, mu, is, g, b, gi,
+                                                k1, k2, slope, has_prelu, use_r, has_gr);
+    if (has_gr) {
       __syncthreads();
-      if (g_stage) stage_planes<NJ, BN_UB>(q.gout, c, n, n1, T, V, shg, TV);
-      if (r_stage) stage_planes<NJ, BN_UB>(q.r, c, n, n1, T, V, shr, TV);
-      __syncthreads();
-    }
+      float* grbase = q.gr.p + (long long)n * q.gr.sn + (long long)c * q.gr.sc;
+      if (gr_mode == 2) {
+        for (int j = 2 * threadIdx.x; j < TV; j += 2 * blockDim.x) {
+          float* grp = grbase + j;
+          const float* po = sho + j;
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      if (tt[i] >= 0) {
-        const int t = tt[i], v = vv[i], e = t * V + v;
-        float yv[BN_UB], rv[BN_UB], gv[BN_UB], mv[BN_UB];
-#pragma unroll
-        for (int u = 0; u < BN_UB; ++u) {
-          const bool ok = n + u < n1;
-          yv[u] = ok ? __ldg(q.y.p + vix(q.y, n + u, c, t, v)) : 0.f;
-          rv[u] = !use_r ? 0.f : r_stage ? shr[u * TV + e] : (ok ? __ldg(q.r.p + vix(q.r, n + u, c, t, v)) : 0.f);
-          gv[u] = g_stage ? shg[u * TV + e] : (ok ? __ldg(q.gout.p + vix(q.gout, n + u, c, t, v)) : 0.f);
-          mv[u] = (q.mask && ok) ? __ldg(q.mask + (((long long)(n + u) * q.C + c) * T + t) * V + v) : 1.f;
+          for (int u = 0; u < U; ++u) {
+            if (u < left) *reinterpret_cast<float2*>(grp) = *reinterpret_cast<const float2*>(po);
+            grp += q.gr.sn;
+            po += TV;
+          }
         }
+      } else {
 #pragma unroll
-        for (int u = 0; u < BN_UB; ++u) {
-          if (n + u < n1) {
-            float xhat, gs;
-            const float gp = bn_gpre(has_prelu, yv[u], rv[u], gv[u], mv[u], mu[i], is[i], g[i], b[i], slope, xhat, gs);
-            q.gy.p[vix(q.gy, n + u, c, t, v)] = g[i] * is[i] * (gp - k1[i] - xhat * k2[i]);
-            if (q.gr.p) {
-              if (gr_stage) sho[u * TV + e] = gp;
-              else q.gr.p[vix(q.gr, n + u, c, t, v)] = gp;
+        for (int i = 0; i < NJ; ++i) {
+          const int pk = tfast_gr ? ps.tf[i] : ps.vf[i];
+          if (pk >= 0) {
+            const int j = threadIdx.x + i * blockDim.x;
+            float* grp = grbase + (gr_mode ? (long long)j : (long long)(pk >> 8) * q.gr.sp + (long long)(pk & 255) * q.gr.sk);
+            const float* po = sho + j;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (u < left) *grp = *po;
+              grp += q.gr.sn;
+              po += TV;
             }
           }
         }
       }
     }
-    if (gr_stage) {
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) {
-        const int j = threadIdx.x + i * blockDim.x;
-        if (j < TV) {
-          int t, v;
-          decode_pos(q.gr, j, T, V, t, v);
-#pragma unroll
-          for (int u = 0; u < BN_UB; ++u)
-            if (n + u < n1) q.gr.p[vix(q.gr, n + u, c, t, v)] = sho[u * TV + t * V + v];
-        }
-      }
-    }
+    __syncthreads();
   }
 }
 
+// U (samples per pipeline stage) is a launch-time choice among the compiled instantiations
+#define DSTD_BN_CASE(kern, NJ_, u, grid, threads, smem, st, q)                       \
+  do {                                                                                \
+    switch (u) {                                                                      \
+      case 4:                                                                         \
+        prefer_smem_carveout((const void*)kern<NJ_, 4>, true);                        \
+        kern<NJ_, 4><<<grid, threads, smem, st>>>(q);                                 \
+        break;                                                                        \
+      case 2:                                                                         \
+        prefer_smem_carveout((const void*)kern<NJ_, 2>, true);                        \
+        kern<NJ_, 2><<<grid, threads, smem, st>>>(q);                                 \
+        break;                                                                        \
+      default:                                                                        \
+        prefer_smem_carveout((const void*)kern<NJ_, 1>, true);                        \
+        kern<NJ_, 1><<<grid, threads, smem, st>>>(q);                                 \
+        break;                                                                        \
+    }                                                                                 \
+  } while (0)
+#define DSTD_BN_DISPATCH_U(kern, nj, u, grid, threads, smem, st, q)                  \
+  do {                                                                                \
+    switch (nj) {                                                                     \
+      case 1: DSTD_BN_CASE(kern, 1, u, grid, threads, smem, st, q); break;            \
+      case 2: DSTD_BN_CASE(kern, 2, u, grid, threads, smem, st, q); break;            \
+      case 4: DSTD_BN_CASE(kern, 4, u, grid, threads, smem, st, q); break;            \
+      default: DSTD_BN_CASE(kern, 8, u, grid, threads, smem, st, q); break;           \
+    }                                                                                 \
+  } while (0)
+
 #define DSTD_BN_DISPATCH(kern, nj, grid, threads, smem, st, q)          \
   do {                                                                  \
-    if ((smem) > 48 * 1024) {                                           \
-      ensure_max_smem((const void*)kern<1>);                            \
-      ensure_max_smem((const void*)kern<2>);                            \
-      ensure_max_smem((const void*)kern<4>);                            \
-      ensure_max_smem((const void*)kern<8>);                            \
-    }                                                                   \
     switch (nj) {                                                       \
       case 1: kern<1><<<grid, threads, smem, st>>>(q); break;           \
       case 2: kern<2><<<grid, threads, smem, st>>>(q); break;           \
@@ -534,22 +866,22 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
   Arena ar(a->ws, a->ws_bytes);
   q.part = ar.take<float>((size_t)q.S * q.C * q.V * 2);
   BnGeom g = bn_geom(q.T, q.V);
-  const size_t sm2 = (size_t)2 * q.T * q.V * sizeof(float);
-  const size_t smu = sm2 * bn_u(g.nj);
+  const size_t tvb = (size_t)q.T * q.V * sizeof(float);
+  const size_t sm2 = 2 * tvb;
+  const int nst = q.r.p ? 2 : 1;                       // staged tensors: y (, r); two pipeline stages
+  const int u = bn_pick_u(tvb, 2 * nst, bn_u_cap(), BN_SMEM_BUDGET);
+  const size_t smu = (size_t)2 * nst * u * tvb;
   const int cv = q.C * q.V;
   if (q.training) {
     DSTD_BN_DISPATCH(bn_stats_kernel, g.nj, dim3(q.C, q.S), g.threads, sm2, st, q);
     count_launch();
     DSTD_LAUNCH_CHECK("bn_stats");
-    bn_finalize_kernel<<<cdiv(cv, 128), 128, 0, st>>>(q);
-    count_launch();
-    DSTD_LAUNCH_CHECK("bn_finalize");
   } else {
     bn_eval_stats_kernel<<<cdiv(cv, 128), 128, 0, st>>>(q);
     count_launch();
     DSTD_LAUNCH_CHECK("bn_eval_stats");
   }
-  DSTD_BN_DISPATCH(bn_apply_kernel, g.nj, dim3(q.C, q.S), g.threads, smu, st, q);
+  DSTD_BN_DISPATCH_U(bn_apply_kernel, g.nj, u, dim3(q.C, q.S), g.threads, smu, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_apply");
   return DSTD_OK;
@@ -580,13 +912,14 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   q.part_p = ar.take<float>((size_t)q.S * q.C);
   BnGeom g = bn_geom(q.T, q.V);
   const size_t tv = (size_t)q.T * q.V * sizeof(float);
-  DSTD_BN_DISPATCH(bn_bwd_reduce_kernel, g.nj, dim3(q.C, q.S), g.threads, 2 * bn_ub(g.nj) * tv, st, q);
+  const int nst = (q.r.p && q.prelu) ? 3 : 2;          // staged tensors: gout, y (, r); two pipeline stages
+  const int ub = bn_pick_u(tv, 2 * nst + 1, bn_ub_cap(), BN_SMEM_BUDGET);
+  size_t sm_red = (size_t)2 * nst * ub * tv;
+  if (sm_red < 2 * tv) sm_red = 2 * tv;
+  DSTD_BN_DISPATCH_U(bn_bwd_reduce_kernel, g.nj, ub, dim3(q.C, q.S), g.threads, sm_red, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_reduce");
-  bn_bwd_finalize_kernel<<<cdiv(q.C * q.V, 256), 256, 0, st>>>(q);
-  count_launch();
-  DSTD_LAUNCH_CHECK("bn_bwd_finalize");
-  DSTD_BN_DISPATCH(bn_bwd_apply_kernel, g.nj, dim3(q.C, q.S), g.threads, 3 * bn_ub(g.nj) * tv, st, q);
+  DSTD_BN_DISPATCH_U(bn_bwd_apply_kernel, g.nj, ub, dim3(q.C, q.S), g.threads, (size_t)(2 * nst + 1) * ub * tv, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_apply");
   return DSTD_OK;

@@ -12,6 +12,7 @@ namespace dstd {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> status (+message)
+void prefer_smem_carveout(const void* kernel, bool need_max);  // largest smem carve-out (+227 KB opt-in if need_max)
 void ensure_max_smem(const void* kernel);  // one-time opt-in to 227 KB dynamic shared memory (capture-safe afterwards)
 constexpr int MAX_DYN_SMEM = 227 * 1024;
 
@@ -90,6 +91,11 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bo
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {   // all but the N most recent groups have landed
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");

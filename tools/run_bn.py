@@ -16,6 +16,7 @@ from dstd_gcn_b200.ops import _out_like  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--reps", type=int, default=20)
     a = ap.parse_args()
     dev, be = torch.device("cuda"), _lib.backend()
     n, c, t, v = a.n, 64, 35, 22
@@ -30,16 +31,27 @@ def main():
     }
     for name, (y, r, order) in cases.items():
         ol = _out_like(y, order)
-        for rep in range(3):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        out, mean, istd = be.bn_act_forward(y, r, gamma, beta, rm, rv, nbt, prelu, None, False, True, 1e-5, 0.1, ol)
+        gout = out    # any tensor with the output's layout
+        be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True)
+        torch.cuda.synchronize()
+        # device time without host gaps: replay each direction as a CUDA graph
+        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gf):
+            be.bn_act_forward(y, r, gamma, beta, rm, rv, nbt, prelu, None, False, True, 1e-5, 0.1, ol)
+        with torch.cuda.graph(gb):
+            be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True)
+        res = []
+        for gr in (gf, gb):
+            gr.replay()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             e[0].record()
-            out, mean, istd = be.bn_act_forward(y, r, gamma, beta, rm, rv, nbt, prelu, None, False, True, 1e-5, 0.1, ol)
+            for _ in range(a.reps):
+                gr.replay()
             e[1].record()
-            gout = out    # any tensor with the output's layout
-            res = be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True)
-            e[2].record()
             torch.cuda.synchronize()
-        print(f"{name}: fwd {e[0].elapsed_time(e[1]) * 1e3:.1f} us  bwd {e[1].elapsed_time(e[2]) * 1e3:.1f} us")
+            res.append(e[0].elapsed_time(e[1]) * 1e3 / a.reps)
+        print(f"{name}: fwd {res[0]:.1f} us  bwd {res[1]:.1f} us")
 
 
 if __name__ == "__main__":
