@@ -77,6 +77,7 @@ class TrainStep:
         # across steps and StepLR updates (engine/prediction.py:193-196,310)
         self.lr_dev = torch.full((1,), self.lr, dtype=self.flat.param.dtype, device=dev)
         self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._grad_tmp = None
         self.graph = None
         self._graph_has_update = False
         self._static = None
@@ -90,19 +91,34 @@ class TrainStep:
         off, n, shape = self.flat.slices[name]
         return self.flat.grad[off:off + n].view(shape)
 
+    def _pass_grads(self, loss, dst):
+        """Gradients of one pass, gathered straight into the flat bucket `dst`.  ``autograd.grad`` hands back one fresh
+        tensor per parameter, so the ~250 per-parameter ``grad += g`` launches of ``backward()`` become one batched
+        concatenation."""
+        params = [p for _, p in self.flat.named]
+        gs = torch.autograd.grad(loss, params, allow_unused=True)
+        torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1) for g, p in zip(gs, params)], out=dst)
+
     def loss_and_grads(self, inputs, inputs_inv, targets):
         n, t, vc = inputs.shape
         v = vc // 3
         scale = 0.5 if self.inverse else 1.0
         self.flat.rebind_grads()
-        self.flat.grad.zero_()
         out = self.model(inputs.view(n, t, v, 3))
         loss = ops.mpjpe(out.reshape(n, t, vc), targets, scale)
+        # the two passes share nothing but the parameters: back-propagate each as soon as its forward is done (the
+        # first pass's saved activations are released before the second forward runs)
+        self._pass_grads(loss, self.flat.grad)
+        loss = loss.detach()
         if self.inverse:
             out_i = self.model(inputs_inv.view(n, t, v, 3))
-            loss = loss + ops.mpjpe(out_i.reshape(n, t, vc), torch.flip(targets, dims=[1]), scale)
-        loss.backward()
-        return loss.detach()
+            loss_i = ops.mpjpe(out_i.reshape(n, t, vc), torch.flip(targets, dims=[1]), scale)
+            if self._grad_tmp is None:
+                self._grad_tmp = torch.empty_like(self.flat.grad)
+            self._pass_grads(loss_i, self._grad_tmp)
+            self.flat.grad.add_(self._grad_tmp)
+            loss = loss + loss_i.detach()
+        return loss
 
     def _finish_step(self):
         """All-reduce of the flat gradient bucket (the path's only collective), optional clip, fused Adam."""
