@@ -70,7 +70,7 @@ static size_t gc_fwd_ws(int Cin, int Cout, int nb, int P = 40, int K = 40) {
 }
 static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   const size_t C1 = Cin + 1, G = (size_t)N * P * K;
-  const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N);
+  const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N, nb);
   const size_t unf = aggmix_bwd_supported(Cin, Cout, P, K, nb) ? 0 : 1;   // buffers only the unfused path needs
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
                      G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, (size_t)(S1 > 296 ? S1 : 296) * 4 * nb * C1 * 4,
@@ -225,7 +225,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
                a->ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const long long G = (long long)N * P * K;
-  const int S1 = wgrad_splits(G), S2 = dynadj_bwd_splits(N);
+  const int S1 = wgrad_splits(G), S2 = dynadj_bwd_splits(N, nb);
   Arena ar(a->ws, a->ws_bytes);
   float* wcat = ar.take<float>((size_t)Cout * nb * C1);
   float* wm = ar.take<float>((size_t)4 * nb * C1);
@@ -297,7 +297,10 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   DynAdjBwdParams db;
   db.N = N; db.P = P; db.K = K; db.nb = nb;
   db.m = a->m; db.pd = a->pd; db.gxm = gxm; db.alpha = a->alpha; db.gm = gm;
-  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) db.w_rm[b] = a->br[b < nb ? b : 0].w_rm;
+  for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {
+    db.w_rm[b] = a->br[b < nb ? b : 0].w_rm;
+    db.b_rm[b] = a->br[b < nb ? b : 0].b_rm;
+  }
   db.S = S2; db.part_wrm = p_wrm; db.part_adj = p_adj; db.part_alpha = p_alpha;
   if ((rc = launch_dynadj_bwd(db, st))) return rc;
 

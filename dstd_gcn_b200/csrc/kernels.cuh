@@ -90,6 +90,7 @@ struct DynAdjBwdParams {
   const float* pd;     // [N,nb,P,K,K]
   const float* gxm;    // [N,nb,P,K,K]
   const float* w_rm[DSTD_MAX_BRANCH];
+  const float* b_rm[DSTD_MAX_BRANCH];
   const float* alpha;  // device scalar or null (=1)
   float* gm;           // [N,nb,4,P,K]
   int S;               // number of batch splits
@@ -97,7 +98,7 @@ struct DynAdjBwdParams {
   float* part_adj;     // [S][nb][K*K]
   float* part_alpha;   // [S][nb]
 };
-int dynadj_bwd_splits(int N);
+int dynadj_bwd_splits(int N, int nb);
 int launch_dynadj_bwd(const DynAdjBwdParams& q, cudaStream_t st);
 bool dynadj_supported(int P, int K);
 
