@@ -323,17 +323,15 @@ __global__ void __launch_bounds__(256, 2) mproj_bwd_kernel(MprojBwdParams q) {
     __syncthreads();   // previous tile's phase 2 done (also orders the wmT staging)
 #pragma unroll
     for (int j = 0; j < 8; ++j) gms[j * MP_LD + tid] = gm[j];
-    // phase 1: gx update + stage x, 4 channels in flight
-    for (int c0 = 0; c0 < Cin; c0 += 4) {
-      float xv[4], gv[4];
+    // phase 1: x tile straight into shared memory with cp.async (all Cin copies of the thread in flight, no
+    // registers), overlapped with the gx read-modify-write, 8 channels in flight
+    for (int c = 0; c < Cin; ++c) cp_async4(xs + c * MP_LD + tid, q.x.p + ox + (long long)c * q.x.sc, ok);
+    for (int c0 = 0; c0 < Cin; c0 += 8) {
+      float gv[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool cok = ok && c0 + u < Cin;
-        xv[u] = cok ? __ldg(q.x.p + ox + (long long)(c0 + u) * q.x.sc) : 0.f;
-        gv[u] = cok ? q.gx.p[og + (long long)(c0 + u) * q.gx.sc] : 0.f;
-      }
+      for (int u = 0; u < 8; ++u) gv[u] = (ok && c0 + u < Cin) ? q.gx.p[og + (long long)(c0 + u) * q.gx.sc] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         if (c0 + u < Cin) {
           const float4 wa = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8);
           const float4 wb = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8 + 4);
@@ -341,10 +339,10 @@ __global__ void __launch_bounds__(256, 2) mproj_bwd_kernel(MprojBwdParams q) {
           s = fmaf(wa.x, gm[0], s); s = fmaf(wa.y, gm[1], s); s = fmaf(wa.z, gm[2], s); s = fmaf(wa.w, gm[3], s);
           s = fmaf(wb.x, gm[4], s); s = fmaf(wb.y, gm[5], s); s = fmaf(wb.z, gm[6], s); s = fmaf(wb.w, gm[7], s);
           if (ok) q.gx.p[og + (long long)(c0 + u) * q.gx.sc] = s;
-          xs[(c0 + u) * MP_LD + tid] = xv[u];
         }
       }
     }
+    cp_async_wait_all();
     xs[Cin * MP_LD + tid] = ok ? 1.0f : 0.f;   // ones row (bias gradients)
     __syncthreads();
     // phase 2: gwm[j][c] += sum_g gm[j][g] x[c][g]
