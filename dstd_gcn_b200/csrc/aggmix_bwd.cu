@@ -150,21 +150,26 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       cp_async_wait_all();
       __syncthreads();
       PH(0);
-      for (int i = tid; i < nb * PCH * K * KP2; i += AMB_NT) {
-        int w = i % KP2, t = i / KP2;
-        int v = t % K;
-        t /= K;
-        int l = t % PCH, b = t / PCH;
-        float val = 0.f, valT = 0.f;
-        if (w < K && l < pv) {
-          const int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
-          const int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
+      // warp = one adjacency row (b, l, v), lanes = w: the (b, l, v) decode is warp-uniform and done once per row
+      for (int b = 0; b < nb; ++b) {
+        const float* ae = aeff + b * KK;
+        for (int r = warp; r < PCH * K; r += AMB_NT / 32) {
+          const int l = r / K, v = r - l * K;
           const float* pr = pdr + (b * PCH + l) * KK;
-          val = fmaf(alpha, pr[e], aeff[b * KK + e]);
-          valT = fmaf(alpha, pr[eT], aeff[b * KK + eT]);
+          float* xr = xms + ((b * PCH + l) * K + v) * KP2;
+          float* xt = xmT + ((b * PCH + l) * K + v) * KP2;
+          for (int w = lane; w < KP2; w += 32) {
+            float val = 0.f, valT = 0.f;
+            if (w < K && l < pv) {
+              const int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
+              const int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
+              val = fmaf(alpha, pr[e], ae[e]);
+              valT = fmaf(alpha, pr[eT], ae[eT]);
+            }
+            xr[w] = val;
+            xt[w] = valT;
+          }
         }
-        xms[i] = val;
-        xmT[i] = valT;
       }
     }
     __syncthreads();
@@ -413,12 +418,23 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
 
     // ---- gx chunk -> HBM (coalesced along the contiguous (l,k) run of each channel)
     {
-      const int npos = pv * K;
+      // warp = channel row, lanes = padded positions (KP is a compile-time constant: no runtime divisions)
+      int poff[TN];
+      bool pok[TN];
+#pragma unroll
+      for (int i = 0; i < TN; ++i) {
+        const int pos = lane + 32 * i;
+        const int l = pos / KP, k = pos - l * KP;
+        pok[i] = pos < npos_pad && l < pv && k < K;
+        poff[i] = pok[i] ? (int)(l * q.gx.sp + k * q.gx.sk) : 0;
+      }
       float* gb = q.gx.p + (long long)n * q.gx.sn + (long long)p0 * q.gx.sp;
-      for (int i = tid; i < Cin * npos; i += AMB_NT) {
-        int c = i / npos, j = i - c * npos;
-        int l = j / K, k = j - l * K;
-        gb[(long long)c * q.gx.sc + (long long)l * q.gx.sp + (long long)k * q.gx.sk] = gxs[c * LD + l * KP + k];
+      for (int c = warp; c < Cin; c += AMB_NT / 32) {
+        const float* src = gxs + c * LD;
+        float* dst = gb + (long long)c * q.gx.sc;
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+          if (pok[i]) dst[poff[i]] = src[lane + 32 * i];
       }
     }
   }
