@@ -174,6 +174,28 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
     }
     __syncthreads();
     PH(1);
+    // The tiles leave no room for a second staging buffer, so the next item's chunk is pulled into L2 instead while
+    // this item computes: its cp.async staging then pays L2 instead of HBM latency.
+    {
+      const long long nxt = item + gridDim.x;
+      if (nxt < nitems) {
+        const int n2 = (int)(nxt / nchunk), q0 = (int)(nxt - (long long)n2 * nchunk) * PCH;
+        const int pv2 = min(PCH, P - q0);
+        auto pf_rows = [&](const float* base, long long row_stride, int rows, int run) {   // rows of `run` floats
+          const int lines = (run * 4 + 127) / 128 + 1;
+          for (int i = tid; i < rows * lines; i += AMB_NT) {
+            const int r = i / lines, li = i - r * lines;
+            const float* a = base + (long long)r * row_stride + min(li * 32, run - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        };
+        if (q.x.sk == 1 && q.x.sp == K)
+          pf_rows(q.x.p + (long long)n2 * q.x.sn + (long long)q0 * q.x.sp, q.x.sc, Cin, pv2 * K);
+        if (q.gout.sk == 1 && q.gout.sp == K)
+          pf_rows(q.gout.p + (long long)n2 * q.gout.sn + (long long)q0 * q.gout.sp, q.gout.sc, Cout, pv2 * K);
+        pf_rows(q.pd + ((long long)n2 * nb * P + q0) * KK, (long long)P * KK, nb, pv2 * KK);
+      }
+    }
 
 #pragma unroll
     for (int b = 0; b < DSTD_MAX_BRANCH; ++b) {   // unrolled: accw[b] must stay in registers
