@@ -198,7 +198,54 @@ class TrainStep:
 def predict(model, inputs):
     """Eval-mode forward on raw ``[N, T, 3V]`` batches (engine/prediction.py:340-353)."""
     n, t, vc = inputs.shape
-    return model(inputs.view(n, t, vc // 3, 3)).reshape(n, t, vc)
+    return model(inputs.view(n, t, vc // 3, 3)).reshape(n, -1, vc)
+
+
+@torch.no_grad()
+def evaluate(model, batches, input_n, eval_frame, dim_used=None, joint_to_ignore=None, joint_equal=None):
+    """Per-frame MPJPE of ``PredictionEngine.test`` (engine/prediction.py:319-430) on the sm_100a forward.
+
+    ``batches`` yields ``(inputs [N, T, 3V], all_seqs [N, T_all, 3J])`` (the 1st and 4th element of the reference's
+    dataset tuple) already on the model's device.  The prediction is scattered into a copy of the ground truth at
+    ``dim_used`` (:374-379), ignored joints take the value of their ``joint_equal`` twin (:385-390), and the metric
+    at output frame ``eval_frame[k]`` is the batch-size-weighted mean joint distance (:395-406).
+    Returns ``(average over all eval frames and batches, per-frame metric)`` like the reference (``t_l.avg, t_metric``)."""
+    eval_frame = [int(j) for j in eval_frame]
+    was_training = model.training
+    model.eval()
+    metric = torch.zeros(len(eval_frame), dtype=torch.float64)
+    total = 0
+    for inputs, all_seqs in batches:
+        outputs = predict(model, inputs.float())
+        all_seqs = all_seqs.float()
+        n, seq_len, _ = all_seqs.shape
+        pred = all_seqs.clone()
+        tail = outputs.shape[1] != seq_len              # model predicts only the frames after input_n
+        if dim_used is not None:
+            idx = torch.as_tensor(dim_used, dtype=torch.long, device=pred.device)
+            if tail:
+                pred[:, input_n:, idx] = outputs
+            else:
+                pred[:, :, idx] = outputs
+        elif tail:
+            pred[:, input_n:] = outputs
+        else:
+            pred[:, :, :] = outputs
+        if joint_to_ignore is not None:
+            ign = torch.as_tensor(joint_to_ignore, dtype=torch.long, device=pred.device)
+            eq = torch.as_tensor(joint_equal, dtype=torch.long, device=pred.device)
+            assert ign.shape == eq.shape
+            pred[:, :, torch.cat((ign * 3, ign * 3 + 1, ign * 3 + 2))] = pred[:, :, torch.cat((eq * 3, eq * 3 + 1, eq * 3 + 2))]
+        p3 = pred.view(n, seq_len, -1, 3)[:, input_n:]
+        t3 = all_seqs.view(n, seq_len, -1, 3)[:, input_n:]
+        fr = torch.as_tensor(eval_frame, dtype=torch.long, device=pred.device)
+        dist_ = torch.linalg.vector_norm(t3[:, fr] - p3[:, fr], dim=-1).mean(dim=(0, 2))   # one device->host read per batch
+        metric += dist_.double().cpu() * n
+        total += n
+    if was_training:
+        model.train()
+    metric /= max(total, 1)
+    return float(metric.mean()), metric.numpy()
 
 
 # ====================================================================================== checkpoints (reference format)
