@@ -133,9 +133,9 @@ template <int TM, int TN>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradParams q) {
   constexpr int KC = 32, PITCH = 36;
   constexpr int BM = 8 * TM, BC = 32 * TN;
+  constexpr int NA = BM * KC / 256, NB = BC * KC / 256;   // values of a tile each thread stages (its column = lane)
   __shared__ __align__(16) float As[BM][PITCH];
   __shared__ __align__(16) float Bs[BC][PITCH];
-  __shared__ long long a_off[KC], b_off[KC];
 
   const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
   const int i0 = blockIdx.y * BM, c0 = blockIdx.z * BC;
@@ -150,37 +150,38 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradParams q) {
 #pragma unroll
     for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
 
+  // software pipeline: the next tile's values are loaded into registers while the current tile is multiplied, so
+  // the global-load latency is paid once per CTA instead of once per 32 columns
+  float ra[NA], rb[NB];
+  auto load_tile = [&](long long gc) {
+    const long long g = gc + lane;
+    long long aoff = -1, boff = -1;
+    if (g < gend) {
+      const int n = (int)(g / PK);
+      const int j = (int)(g - (long long)n * PK);
+      const int p = j / q.K, k = j - p * q.K;
+      aoff = vix(q.a, n, 0, p, k);
+      boff = vix(q.b, n, 0, p, k);
+    }
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+      const int i = i0 + ty + 8 * u;
+      ra[u] = (aoff >= 0 && i < q.M) ? __ldg(q.a.p + aoff + (long long)i * q.a.sc) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int cc = c0 + ty + 8 * u;
+      rb[u] = (boff >= 0 && cc < q.Cd) ? ((cc == q.b_ones_row) ? 1.0f : __ldg(q.b.p + boff + (long long)cc * q.b.sc)) : 0.f;
+    }
+  };
+  if (gbeg < gend) load_tile(gbeg);
   for (long long gc = gbeg; gc < gend; gc += KC) {
-    if (tid < KC) {
-      long long g = gc + tid;
-      if (g < gend) {
-        int n = (int)(g / PK);
-        int j = (int)(g - (long long)n * PK);
-        int p = j / q.K, k = j - p * q.K;
-        a_off[tid] = vix(q.a, n, 0, p, k);
-        b_off[tid] = vix(q.b, n, 0, p, k);
-      } else {
-        a_off[tid] = -1;
-        b_off[tid] = -1;
-      }
-    }
+#pragma unroll
+    for (int u = 0; u < NA; ++u) As[ty + 8 * u][lane] = ra[u];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) Bs[ty + 8 * u][lane] = rb[u];
     __syncthreads();
-    for (int idx = tid; idx < BM * KC; idx += 256) {
-      int i = idx >> 5, kk = idx & 31;
-      long long off = a_off[kk];
-      float v = 0.f;
-      if (off >= 0 && i0 + i < q.M) v = __ldg(q.a.p + off + (long long)(i0 + i) * q.a.sc);
-      As[i][kk] = v;
-    }
-    for (int idx = tid; idx < BC * KC; idx += 256) {
-      int c = idx >> 5, kk = idx & 31;
-      long long off = b_off[kk];
-      int cc = c0 + c;
-      float v = 0.f;
-      if (off >= 0 && cc < q.Cd) v = (cc == q.b_ones_row) ? 1.0f : __ldg(q.b.p + off + (long long)cc * q.b.sc);
-      Bs[c][kk] = v;
-    }
-    __syncthreads();
+    if (gc + KC < gend) load_tile(gc + KC);
 #pragma unroll
     for (int k4 = 0; k4 < KC; k4 += 4) {
       float4 a4[TM], b4[TN];
@@ -214,8 +215,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradParams q) {
 }
 
 int wgrad_splits(long long G) {
-  long long s = (G + 2047) / 2048;
-  if (s > 296) s = 296;
+  long long s = (G + 511) / 512;
+  if (s > 592) s = 592;
   if (s < 1) s = 1;
   return (int)s;
 }
@@ -257,8 +258,15 @@ __global__ void reduce_segments_kernel(ReduceParams q) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int r = idx / s.cols, c = idx - r * s.cols;
     const float* src = s.src + (long long)r * s.src_ld + c;
-    float v = 0.f;
-    for (int k = 0; k < s.S; ++k) v += src[(long long)k * s.sstride];
+    // 8 independent partial sums (8 loads in flight instead of a serial add chain), combined in a fixed order
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= s.S; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += src[(long long)(k + u) * s.sstride];
+    }
+    for (int u = 0; k < s.S; ++k, ++u) a[u] += src[(long long)k * s.sstride];
+    float v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     v *= s.scale;
     if (s.dst) s.dst[(long long)r * s.dst_ld + c] = v;
     if (s.dst2) s.dst2[(long long)r * s.dst_ld + c] = v * __ldg(s.mul + (long long)r * s.dst_ld + c);
