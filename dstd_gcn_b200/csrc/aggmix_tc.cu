@@ -322,17 +322,18 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
 
 // ------------------------------------------------------------------------------------------ weight image for the tensor path
 // wtc[b][hi|lo][tc_off(o, j)]: conv_f weights (+ bias in K row Cin) of branch b as UMMA K-major core matrices, TF32 split
-__global__ void pack_tc_zero_kernel(float* wtc, int nwords) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) wtc[i] = 0.f;
-}
-__global__ void pack_tc_scatter_kernel(PackParams q, float* wtc, int KD, int NP) {
+// One pass over the padded image (NP output rows x KD reduction rows per branch): out-of-range rows are written as
+// zeros, so no separate clear is needed (the 16-byte gaps between core matrices are never read by the MMA).
+__global__ void pack_tc_kernel(PackParams q, float* wtc, int KD, int NP, int* err_flag) {
   const int sbo_f = (KD / 4) * TC_LBO_F, tile = (NP / 8) * sbo_f;
-  const int total = q.nb * q.Cout * (q.Cin + 1);
+  const int total = q.nb * NP * KD;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *err_flag = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i % (q.Cin + 1);
-    int t = i / (q.Cin + 1);
-    const int o = t % q.Cout, b = t / q.Cout;
-    const float w = j < q.Cin ? __ldg(q.w_f[b] + (long long)o * q.Cin + j) : __ldg(q.b_f[b] + o);
+    const int j = i % KD;
+    int t = i / KD;
+    const int o = t % NP, b = t / NP;
+    float w = 0.f;
+    if (o < q.Cout && j <= q.Cin) w = j < q.Cin ? __ldg(q.w_f[b] + (long long)o * q.Cin + j) : __ldg(q.b_f[b] + o);
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(w));
     const float hi = __uint_as_float(h);
@@ -392,10 +393,8 @@ int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cu
   DSTD_REQUIRE(tc_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g, q.skip.p != nullptr), DSTD_ERR_UNSUPPORTED,
                "aggmix_fwd_tc: shape outside limits");
   int* err_flag = reinterpret_cast<int*>(wtc_ws + g.wtc_floats);
-  const int nw = (int)g.wtc_floats + 4;   // image + error flag
-  pack_tc_zero_kernel<<<min(cdiv(nw, 256), 64), 256, 0, st>>>(wtc_ws, nw);
-  pack_tc_scatter_kernel<<<min(cdiv(q.nb * q.Cout * (q.Cin + 1), 256), 64), 256, 0, st>>>(pk, wtc_ws, g.KD, g.NP);
-  count_launch(2);
+  pack_tc_kernel<<<min(cdiv(q.nb * g.NP * g.KD, 256), 64), 256, 0, st>>>(pk, wtc_ws, g.KD, g.NP, err_flag);
+  count_launch();
   DSTD_LAUNCH_CHECK("pack_tc");
   q.PCH = g.PCH;
   q.CoutP = g.NP;

@@ -180,13 +180,17 @@ class _DSTDGCBBase(nn.Module):
             r = ops.bn_act(ops.chmix(x4, _w2(mix.weight), mix.bias), rbn.bn, vc_order=fast)
         else:
             r = x4
+        # unbind (backward = one stack) instead of indexing (backward = zeros + copy per branch + a sum)
+        a_s = self.A_s.unbind(0)
         if fast:
-            brs = [g.branch(self.A_s[i]) for i, g in enumerate(self.conv_s)]
+            brs = [g.branch(a_s[i]) for i, g in enumerate(self.conv_s)]
         else:
-            brs = [g.branch(self.A_s[i], self.W_s[i], self.R_s[i]) for i, g in enumerate(self.conv_s)]
+            w_s, r_s = self.W_s.unbind(0), self.R_s.unbind(0)
+            brs = [g.branch(a_s[i], w_s[i], r_s[i]) for i, g in enumerate(self.conv_s)]
         y = ops.gc_unit(x4, self.alpha_sm, brs, adj_t=fast)
         x2 = ops.bn_act(y, self.bn.bn, r=r, prelu=self.prelu.weight, vc_order=fast, out_order=ops.ORDER_V_MAJOR)
-        brt = [g.branch(self.A_t[i], None, self.R_t[i]) for i, g in enumerate(self.conv_t)]
+        a_t, r_t = self.A_t.unbind(0), self.R_t.unbind(0)
+        brt = [g.branch(a_t[i], None, r_t[i]) for i, g in enumerate(self.conv_t)]
         skip_u = None if skip4 is None else skip4.permute(0, 1, 3, 2)
         z_u = ops.gc_unit(x2.permute(0, 1, 3, 2), self.alpha_tm, brt, skip_u=skip_u, adj_t=fast)
         return z_u.permute(0, 1, 3, 2)
