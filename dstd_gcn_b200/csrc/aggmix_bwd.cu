@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   float* xs = smem;                         // [C1R8][LD]  (row Cin = ones on valid positions, rows above: zero)
   float* gos = xs + C1R8 * LD;              // [CoutR16][LD]
   const int CoutR8 = (Cout + 7) & ~7, CoutR16 = (Cout + 15) & ~15;
-  const int WS = q.WS;                      // weight row stride: >= round16(Cin), == 8 (mod 32)
+  const int WS = q.WS;                      // weight row stride: >= round16(Cin), == 4 (mod 32)
   float* gxas = gos + CoutR16 * LD;         // [C1R8][LD]  (rows above Cin: zero)
   float* xas = gxas + C1R8 * LD;            // [C1][LD]
   float* gxs = xas + C1 * LD;               // [Cin][LD]
@@ -211,18 +211,20 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
 #pragma unroll
           for (int i = 0; i < TN; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
           for (int k0 = 0; k0 < CoutR8; k0 += 8) {
-            const float* wr = wb + (k0 + ft) * WS + m0 + fg;
+            // k-slot permutation (slot t <-> row 2t, slot t+4 <-> row 2t+1, same for A and B): with LD == 4 (mod 8)
+            // and WS == 4 (mod 32) the four k rows of a load land 8 banks apart -> conflict-free fragment loads
+            const float* wr = wb + (k0 + 2 * ft) * WS + m0 + fg;
             uint32_t ah[4], al[4];
             split3(wr[0], ah[0], al[0]);
             split3(wr[8], ah[1], al[1]);
-            split3(wr[4 * WS], ah[2], al[2]);
-            split3(wr[4 * WS + 8], ah[3], al[3]);
-            const float* gr = gos + (k0 + ft) * LD + n0 + fg;
+            split3(wr[WS], ah[2], al[2]);
+            split3(wr[WS + 8], ah[3], al[3]);
+            const float* gr = gos + (k0 + 2 * ft) * LD + n0 + fg;
 #pragma unroll
             for (int i = 0; i < TN; ++i) {
               uint32_t bh[2], bl[2];
               split3(gr[i * 8], bh[0], bl[0]);
-              split3(gr[i * 8 + 4 * LD], bh[1], bl[1]);
+              split3(gr[i * 8 + LD], bh[1], bl[1]);
               mma_tf32(acc[i], ah, bh);
               mma_tf32(acc[i], ah, bl);
               mma_tf32(acc[i], al, bh);
@@ -239,11 +241,17 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
           }
         }
         // bias row: gxa[Cin][pos] = sum_o bf[o] gout[o][pos]   (warp = positions, lanes = output channels)
-        for (int pos = warp; pos < npos_pad; pos += AMB_NT / 32) {
+        // warp = 4 positions x 8 interleaved channel groups (o = 8 i + lane/4): with LD == 4 (mod 8) the 32 lanes hit
+        // 32 banks; the 8 partial sums of a position are combined by a fixed butterfly
+        for (int p4 = warp * 4; p4 < npos_pad; p4 += (AMB_NT / 32) * 4) {
+          const int pos = p4 + (lane & 3), og = lane >> 2;
           float sres = 0.f;
-          for (int o = lane; o < Cout; o += 32) sres = fmaf(bfs[b * Cout + o], gos[o * LD + pos], sres);
-          sres = warp_sum(sres);
-          if (lane == 0) gxas[Cin * LD + pos] = sres;
+          if (pos < npos_pad)
+            for (int o = og; o < Cout; o += 8) sres = fmaf(bfs[b * Cout + o], gos[o * LD + pos], sres);
+          sres += __shfl_xor_sync(0xffffffffu, sres, 4);
+          sres += __shfl_xor_sync(0xffffffffu, sres, 8);
+          sres += __shfl_xor_sync(0xffffffffu, sres, 16);
+          if (og == 0 && pos < npos_pad) gxas[Cin * LD + pos] = sres;
         }
       }
 
@@ -401,19 +409,19 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
           float acc[NH][4];
 #pragma unroll
           for (int i = 0; i < NH; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-          const float* ar = xs + ft * LD + l * KP + m0 + fg;
-          const float* br = gxas + ft * LD + l * KP + nh * NH * 8 + fg;
+          const float* ar = xs + 2 * ft * LD + l * KP + m0 + fg;     // same k-slot permutation as in (a)
+          const float* br = gxas + 2 * ft * LD + l * KP + nh * NH * 8 + fg;
           for (int k0 = 0; k0 < C1R8; k0 += 8) {
             uint32_t ah[4], al[4];
             split3(ar[k0 * LD], ah[0], al[0]);
             split3(ar[k0 * LD + 8], ah[1], al[1]);
-            split3(ar[(k0 + 4) * LD], ah[2], al[2]);
-            split3(ar[(k0 + 4) * LD + 8], ah[3], al[3]);
+            split3(ar[(k0 + 1) * LD], ah[2], al[2]);
+            split3(ar[(k0 + 1) * LD + 8], ah[3], al[3]);
 #pragma unroll
             for (int i = 0; i < NH; ++i) {
               uint32_t bh[2], bl[2];
               split3(br[k0 * LD + i * 8], bh[0], bl[0]);
-              split3(br[(k0 + 4) * LD + i * 8], bh[1], bl[1]);
+              split3(br[(k0 + 1) * LD + i * 8], bh[1], bl[1]);
               mma_tf32(acc[i], ah, bh);
               mma_tf32(acc[i], ah, bl);
               mma_tf32(acc[i], al, bh);
@@ -504,7 +512,7 @@ static bool aggmix_bwd_geom(int Cin, int Cout, int P, int K, int nb, AggMixBwdGe
   const int WH = (g.KP / 2 + 3) / 4 * 4, KP2 = 2 * WH, C1 = Cin + 1;
   g.CinP = (Cin + 7) / 8 * 8;
   g.WS = (Cin + 15) / 16 * 16;
-  while (g.WS % 32 != 8) g.WS += 8;          // conflict-free A-fragment loads: row stride == 8 (mod 32)
+  while (g.WS % 32 != 4) g.WS += 4;          // conflict-free A-fragment loads of (a): row stride == 4 (mod 32)
   const int CoutR8 = (Cout + 7) / 8 * 8, CoutR16 = (Cout + 15) / 16 * 16;
   if ((CoutR16 / 16) * ((Cin + 15) / 16) > AMB_NT / 32) return false;   // (c): one warp per (16 x 16) gradient tile pair
   for (int pch = 128 / g.KP; pch >= 1; --pch) {
