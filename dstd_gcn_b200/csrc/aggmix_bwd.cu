@@ -150,26 +150,21 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       cp_async_wait_all();
       __syncthreads();
       PH(0);
-      // warp = one adjacency row (b, l, v), lanes = w: the (b, l, v) decode is warp-uniform and done once per row
-      for (int b = 0; b < nb; ++b) {
-        const float* ae = aeff + b * KK;
-        for (int r = warp; r < PCH * K; r += AMB_NT / 32) {
-          const int l = r / K, v = r - l * K;
+      for (int i = tid; i < nb * PCH * K * KP2; i += AMB_NT) {
+        int w = i % KP2, t = i / KP2;
+        int v = t % K;
+        t /= K;
+        int l = t % PCH, b = t / PCH;
+        float val = 0.f, valT = 0.f;
+        if (w < K && l < pv) {
+          const int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
+          const int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
           const float* pr = pdr + (b * PCH + l) * KK;
-          float* xr = xms + ((b * PCH + l) * K + v) * KP2;
-          float* xt = xmT + ((b * PCH + l) * K + v) * KP2;
-          for (int w = lane; w < KP2; w += 32) {
-            float val = 0.f, valT = 0.f;
-            if (w < K && l < pv) {
-              const int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
-              const int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
-              val = fmaf(alpha, pr[e], ae[e]);
-              valT = fmaf(alpha, pr[eT], ae[eT]);
-            }
-            xr[w] = val;
-            xt[w] = valT;
-          }
+          val = fmaf(alpha, pr[e], aeff[b * KK + e]);
+          valT = fmaf(alpha, pr[eT], aeff[b * KK + eT]);
         }
+        xms[i] = val;
+        xmT[i] = valT;
       }
     }
     __syncthreads();
