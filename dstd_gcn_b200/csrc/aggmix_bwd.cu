@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   float* bfs = wfB + nb * CoutR8 * WS;      // [nb][Cout]
   float* aeff = bfs + ((nb * Cout + 3) & ~3);   // [nb][K*K]    static adjacency A*W + R
   float* pdr = aeff + ((nb * KK + 3) & ~3);     // [nb][PCH][K*K] raw dynamic adjacency of the current item
+  int* rowtab = reinterpret_cast<int*>(pdr + ((nb * PCH * KK + 3) & ~3));   // [nb*PCH*K]  (b*PCH + l) << 8 | v per row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
   const int nchunk = (P + PCH - 1) / PCH;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
     xs[C1 * LD + i] = 0.f;
     gxas[C1 * LD + i] = 0.f;
   }
+  for (int i = tid; i < nb * PCH * K; i += AMB_NT) rowtab[i] = ((i / K) << 8) | (i % K);
   for (int i = tid; i < nb * Cout; i += AMB_NT) bfs[i] = __ldg(q.b_f[i / Cout] + (i % Cout));
   for (int i = tid; i < nb * KK; i += AMB_NT) {
     const int b = i / KK, e = i - b * KK;
@@ -150,16 +152,17 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
       cp_async_wait_all();
       __syncthreads();
       PH(0);
+      // element-parallel (8 independent elements per thread); the row decode comes from a table built once per CTA, so
+      // there is no runtime division in the loop (KP2 is a compile-time constant)
       for (int i = tid; i < nb * PCH * K * KP2; i += AMB_NT) {
-        int w = i % KP2, t = i / KP2;
-        int v = t % K;
-        t /= K;
-        int l = t % PCH, b = t / PCH;
+        const int row = i / KP2, w = i - row * KP2;
+        const int info = rowtab[row], bl = info >> 8, v = info & 255;   // bl = b * PCH + l
+        const int b = bl >= PCH ? (bl >= 2 * PCH ? 2 : 1) : 0, l = bl - b * PCH;
         float val = 0.f, valT = 0.f;
         if (w < K && l < pv) {
           const int e = q.adj_t ? (w * K + v) : (v * K + w);      // xmu[v][w]
           const int eT = q.adj_t ? (v * K + w) : (w * K + v);     // xmu[w][v]
-          const float* pr = pdr + (b * PCH + l) * KK;
+          const float* pr = pdr + bl * KK;
           val = fmaf(alpha, pr[e], aeff[b * KK + e]);
           valT = fmaf(alpha, pr[eT], aeff[b * KK + eT]);
         }
@@ -517,7 +520,7 @@ static bool aggmix_bwd_geom(int Cin, int Cout, int P, int K, int nb, AggMixBwdGe
     if ((ld / 4) % 2 == 0) ld += 4;
     const int C1R8 = (C1 + 7) / 8 * 8;
     size_t f = (size_t)(2 * C1R8 + C1 + CoutR16 + Cin) * ld + (size_t)2 * nb * pch * K * KP2 + (size_t)nb * CoutR8 * g.WS +
-               (size_t)nb * Cout + (size_t)nb * K * K * (pch + 1) + 32;
+               (size_t)nb * Cout + (size_t)nb * K * K * (pch + 1) + (size_t)nb * pch * K + 40;
     if (f * sizeof(float) <= (size_t)MAX_DYN_SMEM - 512) {
       g.PCH = pch;
       g.LD = ld;

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
   float* pdr = aeff + ((nb * KK + 3) & ~3);          // [nb][PCH][K*K]
   // layer-skip chunk [Cout][XS_LD] (only when a skip is fused): staged with the lanes walking the SKIP tensor's own
   // contiguous direction, because the skip is kept in the other memory order (it is the block input)
-  float* sks = pdr + ((nb * PCH * KK + 3) & ~3);
+  int* rowtab = reinterpret_cast<int*>(pdr + ((nb * PCH * KK + 3) & ~3));   // [nb*PCH*K]  (b*PCH + l) << 8 | v per row
+  float* sks = reinterpret_cast<float*>(rowtab + ((nb * PCH * K + 3) & ~3));
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sks + (q.skip.p ? ((Cout * XS_LD + 3) & ~3) : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = tid; i < nb * PCH * K; i += TC_NT) rowtab[i] = ((i / K) << 8) | (i % K);
     cp_async_wait_all();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -178,15 +180,15 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
       }
       cp_async_wait_all();
       __syncthreads();
+      // element-parallel; the row decode comes from a table built once per CTA (no runtime division in the loop)
       for (int i = tid; i < nb * PCH * K * KP; i += TC_NT) {
-        int w = i % KP, t = i / KP;
-        int v = t % K;
-        t /= K;
-        int l = t % PCH, b = t / PCH;
+        const int row = i / KP, w = i - row * KP;
+        const int info = rowtab[row], bl = info >> 8, v = info & 255;   // bl = b * PCH + l
+        const int b = bl >= PCH ? 1 : 0, l = bl - b * PCH;
         float val = 0.f;
         if (w < K && l < pv) {
           const int e = q.adj_t ? (w * K + v) : (v * K + w);
-          val = fmaf(alpha, pdr[(b * PCH + l) * KK + e], aeff[b * KK + e]);
+          val = fmaf(alpha, pdr[bl * KK + e], aeff[b * KK + e]);
         }
         xms[i] = val;
       }
@@ -361,7 +363,7 @@ static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g, bool wit
     if (pch > P && pch > 1) continue;
     const int XS_LD = (pch * K) | 1;
     size_t f = (size_t)2 * ((pch * K + 7) / 8) * sbo_f + g.wtc_floats + (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * pch * K * KP +
-               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + 8 +
+               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + (size_t)((nb * pch * K + 3) & ~3) + 8 +
                (with_skip ? (size_t)((Cout * XS_LD + 3) & ~3) : 0);
     // the M = 128 descriptors read 16 row groups from each A tile: keep that window inside the allocation
     const size_t a_window = (size_t)((pch * K + 7) / 8) * sbo_f + (size_t)16 * sbo_f + 64;
