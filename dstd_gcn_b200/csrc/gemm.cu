@@ -252,24 +252,40 @@ int launch_wgrad(WgradParams& q, cudaStream_t st) {
 }
 
 // ================================================================================= reduce + scatter
-__global__ void reduce_segments_kernel(ReduceParams q) {
+// block = 8 warps: warp w sums the w-th eighth of the S partials for 32 consecutive outputs (coalesced 128-byte
+// loads, 4 in flight), the eight sub-sums are combined in a fixed order through shared memory (deterministic).  A
+// single thread per output walking all S partials was a chain of ~S/8 dependent L2 round trips (22-25 us per call).
+__global__ void __launch_bounds__(256) reduce_segments_kernel(ReduceParams q) {
+  __shared__ float part[8][32];
   const ReduceSeg& s = q.seg[blockIdx.y];
-  int total = s.rows * s.cols;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    int r = idx / s.cols, c = idx - r * s.cols;
-    const float* src = s.src + (long long)r * s.src_ld + c;
-    // 8 independent partial sums (8 loads in flight instead of a serial add chain), combined in a fixed order
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int k = 0;
-    for (; k + 8 <= s.S; k += 8) {
+  const int total = s.rows * s.cols, lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+  const int per = (s.S + 7) / 8, k0 = ch * per, k1 = min(s.S, k0 + per);
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int idx = base + lane;
+    const int r = idx / s.cols, c = idx - r * s.cols;
+    float v = 0.f;
+    if (idx < total) {
+      const float* src = s.src + (long long)r * s.src_ld + c;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      int k = k0;
+      for (; k + 4 <= k1; k += 4) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += src[(long long)(k + u) * s.sstride];
+        for (int u = 0; u < 4; ++u) a[u] += src[(long long)(k + u) * s.sstride];
+      }
+      for (int u = 0; k < k1; ++k, ++u) a[u] += src[(long long)k * s.sstride];
+      v = (a[0] + a[1]) + (a[2] + a[3]);
     }
-    for (int u = 0; k < s.S; ++k, ++u) a[u] += src[(long long)k * s.sstride];
-    float v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    v *= s.scale;
-    if (s.dst) s.dst[(long long)r * s.dst_ld + c] = v;
-    if (s.dst2) s.dst2[(long long)r * s.dst_ld + c] = v * __ldg(s.mul + (long long)r * s.dst_ld + c);
+    part[ch][lane] = v;
+    __syncthreads();
+    if (ch == 0 && idx < total) {
+      float t = part[0][lane];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t += part[j][lane];
+      t *= s.scale;
+      if (s.dst) s.dst[(long long)r * s.dst_ld + c] = t;
+      if (s.dst2) s.dst2[(long long)r * s.dst_ld + c] = t * __ldg(s.mul + (long long)r * s.dst_ld + c);
+    }
+    __syncthreads();
   }
 }
 
@@ -277,8 +293,8 @@ int launch_reduce(const ReduceParams& q, cudaStream_t st) {
   if (q.nseg == 0) return 0;
   int maxe = 1;
   for (int i = 0; i < q.nseg; ++i) maxe = max(maxe, q.seg[i].rows * q.seg[i].cols);
-  dim3 grid(min(cdiv(maxe, 128), 64), q.nseg);
-  reduce_segments_kernel<<<grid, 128, 0, st>>>(q);
+  dim3 grid(min(cdiv(maxe, 32), 128), q.nseg);
+  reduce_segments_kernel<<<grid, 256, 0, st>>>(q);
   count_launch();
   return check_launch("reduce_segments");
 }
