@@ -348,14 +348,14 @@ __global__ void __launch_bounds__(256, 2) mproj_bwd_kernel(MprojBwdParams q) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) gms[j * MP_LD + tid] = gm[j];
     // phase 1: x tile straight into shared memory with cp.async (all Cin copies of the thread in flight, no
-    // registers), overlapped with the gx read-modify-write, 8 channels in flight
+    // registers), overlapped with the gx read-modify-write, 16 channels in flight
     for (int c = 0; c < Cin; ++c) cp_async4(xs + c * MP_LD + tid, q.x.p + ox + (long long)c * q.x.sc, ok);
-    for (int c0 = 0; c0 < Cin; c0 += 8) {
-      float gv[8];
+    for (int c0 = 0; c0 < Cin; c0 += 16) {
+      float gv[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) gv[u] = (ok && c0 + u < Cin) ? q.gx.p[og + (long long)(c0 + u) * q.gx.sc] : 0.f;
+      for (int u = 0; u < 16; ++u) gv[u] = (ok && c0 + u < Cin) ? q.gx.p[og + (long long)(c0 + u) * q.gx.sc] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {
         if (c0 + u < Cin) {
           const float4 wa = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8);
           const float4 wb = *reinterpret_cast<const float4*>(wmT + (c0 + u) * 8 + 4);
