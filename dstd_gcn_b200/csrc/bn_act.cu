@@ -169,8 +169,48 @@ __device__ __forceinline__ int slot_of(bool tfast, int t, int v, int T, int V) {
 // cp.async samples n .. n+U-1 (`left` of them exist) of channel plane c of `w` into the [U][T*V] region at shared
 // address `sdst`, each plane in w's own memory order
 template <int NJ, int U, bool FULL>
-__device__ __forceinline__ void stage_async(const Pos2<NJ>& ps, const View4& w, int c, int n, int left, unsigned sdst,
-                                            int T, int V) {
+__device__ __forceinline__ void stage_async(const Pos2<NJ>& ps, const View4& w, int mode, int c, int n, int left,
+                                            unsigned sdst, int T, int V) {
+  const int TV = T * V;
+  const float* base = w.p + (long long)n * w.sn + (long long)c * w.sc;
+  if (mode == 2) {
+    // the launch geometry gives NJ * blockDim >= T*V, so for NJ <= 2 a thread owns at most one pair of positions
+    for (int j = 2 * threadIdx.x; j < TV; j += 2 * blockDim.x) {
+      const float* p = base + j;
+      unsigned d = sdst + (unsigned)j * 4u;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) cp_async8_s(d, p);
+        p += w.sn;
+        d += (unsigned)TV * 4u;
+      }
+      if (NJ <= 2) break;
+    }
+  } else {
+    const bool tfast = t_fastest(w);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int pk = tfast ? ps.tf[i] : ps.vf[i];
+      if (pk >= 0) {
+        const int j = threadIdx.x + i * blockDim.x;
+        const float* p = base + (mode ? (long long)j : (long long)(pk >> 8) * w.sp + (long long)(pk & 255) * w.sk);
+        unsigned d = sdst + (unsigned)j * 4u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (FULL || u < left) cp_async4_s(d, p);
+          p += w.sn;
+          d += (unsigned)TV * 4u;
+        }
+      }
+    }
+  }
+}
+
+// backward kernels: same copy, plane mode derived at the call (they sit at the 64-register cap and measured slower
+// with the hoisted mode / single-pair form of the forward)
+template <int NJ, int U, bool FULL>
+__device__ __forceinline__ void stage_async_b(const Pos2<NJ>& ps, const View4& w, int c, int n, int left, unsigned sdst,
+                                              int T, int V) {
   const int TV = T * V, mode = plane_mode(w, T, V);
   const float* base = w.p + (long long)n * w.sn + (long long)c * w.sc;
   if (mode == 2) {
@@ -374,15 +414,16 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_apply_kernel(BnFwdP q) {
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
   Pos2<NJ> ps;
   pos_init<NJ>(ps, T, V, TV);
+  const int mode_y = plane_mode(q.y, T, V), mode_r = has_r ? plane_mode(q.r, T, V) : 0;
   auto issue = [&](int it) {
     const unsigned d = sbase + (unsigned)((it & 1) * stage_f) * 4u;
     const int n = n0 + it * U, left = n1 - n;
     if (left >= U) {
-      stage_async<NJ, U, true>(ps, q.y, c, n, left, d, T, V);
-      if (has_r) stage_async<NJ, U, true>(ps, q.r, c, n, left, d + (unsigned)(U * TV) * 4u, T, V);
+      stage_async<NJ, U, true>(ps, q.y, mode_y, c, n, left, d, T, V);
+      if (has_r) stage_async<NJ, U, true>(ps, q.r, mode_r, c, n, left, d + (unsigned)(U * TV) * 4u, T, V);
     } else {
-      stage_async<NJ, U, false>(ps, q.y, c, n, left, d, T, V);
-      if (has_r) stage_async<NJ, U, false>(ps, q.r, c, n, left, d + (unsigned)(U * TV) * 4u, T, V);
+      stage_async<NJ, U, false>(ps, q.y, mode_y, c, n, left, d, T, V);
+      if (has_r) stage_async<NJ, U, false>(ps, q.r, mode_r, c, n, left, d + (unsigned)(U * TV) * 4u, T, V);
     }
   };
   if (iters > 0) issue(0);
@@ -535,13 +576,13 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_reduce_kernel(BnBwdP
     const unsigned d = sbase + (unsigned)((it & 1) * stage_f) * 4u, du = (unsigned)(U * TV) * 4u;
     const int n = n0 + it * U, left = n1 - n;
     if (left >= U) {
-      stage_async<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
-      stage_async<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
-      if (use_r) stage_async<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
+      stage_async_b<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
+      stage_async_b<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async_b<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
     } else {
-      stage_async<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
-      stage_async<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
-      if (use_r) stage_async<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
+      stage_async_b<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
+      stage_async_b<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async_b<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
     }
   };
   if (iters > 0) issue(0);
@@ -677,13 +718,13 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
     const unsigned d = sbase + (unsigned)((it & 1) * stage_f) * 4u, du = (unsigned)(U * TV) * 4u;
     const int n = n0 + it * U, left = n1 - n;
     if (left >= U) {
-      stage_async<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
-      stage_async<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
-      if (use_r) stage_async<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
+      stage_async_b<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
+      stage_async_b<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async_b<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
     } else {
-      stage_async<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
-      stage_async<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
-      if (use_r) stage_async<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
+      stage_async_b<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
+      stage_async_b<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
+      if (use_r) stage_async_b<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
     }
   };
   if (iters > 0) issue(0);
