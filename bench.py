@@ -35,6 +35,37 @@ WORKLOADS = {
 C_FEAT, N_LAYERS = 64, 5
 
 
+def dominant_call_roofline(batch, v, t, peak, c=C_FEAT, reps=5):
+    """Live CUDA-event timing of the dominant ABI call of the step, `dstd_gc_backward` of an encoder's spatial unit
+    (aggmix_bwd + dynadj_bwd + mproj_bwd: ~45 % of the step), against its own algorithmic bytes: x and the output
+    gradient are read once, the input gradient is written once (3 activation tiles per sample, fp32)."""
+    import torch
+    from dstd_gcn_b200 import _lib
+    dev, be = torch.device("cuda"), _lib.backend()
+    g = torch.Generator().manual_seed(1)
+    r = lambda *s, sc=0.2: (torch.randn(*s, generator=g) * sc).to(dev)
+    brs = [dict(w_m1=r(2, c, 1, 1), b_m1=r(2), w_m2=r(2, c, 1, 1), b_m2=r(2), w_rm=r(t, 2 * t, 1, 1), b_rm=r(t),
+                w_f=r(c, c, 1, 1), b_f=r(c), adj=(torch.rand(v, v, generator=g) > 0.7).float().to(dev), adj_w=r(v, v),
+                adj_r=r(v, v)) for _ in range(2)]
+    x, go, alpha = r(batch, c, t, v, sc=1.0), r(batch, c, t, v, sc=1.0), torch.tensor([0.3], device=dev)
+    out, m, pd, xa = be.gc_forward(x, alpha, brs, None, False)
+    xa = xa if xa.numel() else None
+    be.gc_backward(x, go, alpha, brs, m, pd, xa, False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        be.gc_backward(x, go, alpha, brs, m, pd, xa, False)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    nbytes = 3 * batch * c * t * v * 4
+    ach = nbytes / (us * 1e-6) / 1e9
+    return {"call": "dstd_gc_backward, encoder spatial unit (2 branches)", "avg_us": us,
+            "algorithmic_bytes_per_call": nbytes, "achieved": ach, "unit": "GB/s", "frac": ach / peak,
+            "calls_per_step": 2 * N_LAYERS}
+
+
 def algorithmic_bytes_per_pass(v, t, c=C_FEAT, layers=N_LAYERS):
     """one HBM round trip per DSTDGCB layer, fp32, forward + backward of one model pass."""
     chans = [(6, c)] + [(c, c)] * layers + [(c, 3)]
@@ -414,6 +445,10 @@ def main():
                                   f"layer fwd+bwd = {bytes_pass} B per model pass (SURVEY.md 8d), 2 passes per sample",
                          "algorithmic_bytes_per_sample": 2 * bytes_pass},
         }
+        try:
+            line["roofline"]["dominant_call"] = dominant_call_roofline(args.batch, v, t, peak)
+        except Exception as e:      # never lose the bench line over the extra measurement
+            line["roofline"]["dominant_call"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cb = 32
