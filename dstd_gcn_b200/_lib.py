@@ -71,7 +71,7 @@ class BnBwdArgs(C.Structure):
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("prelu", C.c_void_p), ("mask", C.c_void_p),
                 ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p),
                 ("ggamma", C.c_void_p), ("gbeta", C.c_void_p), ("gprelu", C.c_void_p),
-                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t), ("gr_add", View)]
 
 
 class ChmixFwdArgs(C.Structure):
@@ -290,7 +290,7 @@ class CudaBackend:
         return out, save_mean, save_invstd
 
     def bn_act_backward(self, y, r, gout, gamma, beta, prelu, mask, save_mean, save_invstd, vc_order, training,
-                        need_gr=True):
+                        need_gr=True, gr_add=None):
         n, c, t, v = y.shape
         dev = y.device
         gy = torch.empty_like(y)
@@ -304,6 +304,7 @@ class CudaBackend:
         a.vc_order, a.training = int(vc_order), int(training)
         a.y, a.r, a.gout = _view(y, "y"), _view(r, "r"), _view(gout, "gout")
         a.gy, a.gr = _view(gy, "gy"), _view(gr, "gr")
+        a.gr_add = _view(gr_add if gr is not None else None, "gr_add")
         a.gamma, a.beta = _cptr(gamma, "gamma"), _cptr(beta, "beta")
         a.prelu, a.mask = _cptr(prelu, "prelu"), _cptr(mask, "mask")
         a.save_mean, a.save_invstd = _cptr(save_mean, "save_mean"), _cptr(save_invstd, "save_invstd")

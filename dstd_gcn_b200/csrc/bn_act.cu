@@ -36,7 +36,7 @@ static int bn_ub_cap() {       // backward kernels
   static const int u = bn_env("DSTD_BN_UB", 4);
   return u;
 }
-static const size_t BN_SMEM_BUDGET = 100 * 1024;   // two CTAs per SM
+static const size_t BN_SMEM_BUDGET = 111 * 1024;   // two CTAs per SM (9 planes of 4 samples at H3.6M = 110.9 KB)
 
 int bn_act_splits(int N, int C) {
   (void)C;
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_apply_kernel(BnFwdP q) {
 // ------------------------------------------------------------------------------------------ backward
 struct BnBwdP {
   int N, C, T, V, vc_order, training, S;
-  View4 y, r, gout, gy, gr;
+  View4 y, r, gout, gy, gr, gadd;
   const float *gamma, *beta, *prelu, *mask, *save_mean, *save_invstd;
   float *ggamma, *gbeta, *gprelu;
   float* part;    // [S][C][V][2]
@@ -657,10 +657,11 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_reduce_kernel(BnBwdP
 
 // pass 2: gy (and gr).  Positions in gy's memory order; y, gout and r come through shared memory (cp.async,
 // double-buffered), gr leaves through it.
-template <int NJ, int U, bool FULL, bool MASK>
+template <int NJ, int U, bool FULL, bool MASK, bool ADD>
 __device__ __forceinline__ void bn_bwd_apply_consume(const BnBwdP& q, const float* stage, float* sho, float* (&gyp)[NJ],
                                                      const int (&sg)[NJ], const int (&sy)[NJ], const int (&sr)[NJ],
-                                                     const int (&so)[NJ], const int (&me)[NJ], int c, int n, int left,
+                                                     const int (&so)[NJ], const int (&sa)[NJ], int add_region,
+                                                     const int (&me)[NJ], int c, int n, int left,
                                                      const float (&mu)[NJ], const float (&is)[NJ],
                                                      const float (&g)[NJ], const float (&b)[NJ],
                                                      const float (&gi)[NJ], const float (&k1)[NJ],
@@ -674,6 +675,7 @@ __device__ __forceinline__ void bn_bwd_apply_consume(const BnBwdP& q, const floa
       const float* pg = stage + sg[i];
       const float* py = stage + U * TV + sy[i];
       const float* pr = stage + 2 * U * TV + sr[i];
+      const float* pa = ADD ? stage + add_region * U * TV + sa[i] : stage;
       float* po = sho + so[i];
       float* o = gyp[i];
 #pragma unroll
@@ -684,12 +686,13 @@ __device__ __forceinline__ void bn_bwd_apply_consume(const BnBwdP& q, const floa
           float xhat, gs;
           const float gp = bn_gpre(has_prelu, *py, rv, *pg, mv, mu[i], is[i], g[i], b[i], slope, xhat, gs);
           *o = gi[i] * (gp - k1[i] - xhat * k2[i]);
-          if (has_gr) *po = gp;
+          if (has_gr) *po = ADD ? gp + *pa : gp;
         }
         o += gysn;
         pg += TV;
         py += TV;
         pr += TV;
+        if (ADD) pa += TV;
         po += TV;
       }
       gyp[i] = o;
@@ -697,9 +700,9 @@ __device__ __forceinline__ void bn_bwd_apply_consume(const BnBwdP& q, const floa
   }
 }
 
-template <int NJ, int U>
-__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP q) {
-  extern __shared__ float sh[];   // [2 stages][nst = 2 (gout, y) or 3 (+ r)][U][T*V], then [U][T*V] for gr
+template <int NJ, int U, bool ADD>
+__device__ __forceinline__ void bn_bwd_apply_body(const BnBwdP& q) {
+  extern __shared__ float sh[];   // [2 stages][nst = 2 (gout, y), + r, + gr_add][U][T*V], then [U][T*V] for gr
   const int c = blockIdx.x, s = blockIdx.y, T = q.T, V = q.V, TV = T * V;
   const int n0 = (int)((long long)q.N * s / q.S), n1 = (int)((long long)q.N * (s + 1) / q.S), cnt = n1 - n0;
   const bool has_prelu = q.prelu != nullptr;
@@ -707,7 +710,9 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
   const bool has_gr = q.gr.p != nullptr;
   const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
   const float icnt = 1.0f / ((float)q.N * (float)T);
-  const int stage_f = (use_r ? 3 : 2) * U * TV, iters = (cnt + U - 1) / U;
+  const bool has_add = ADD;       // the host launches the ADD instantiation only with gr and gr_add present
+  const int add_region = has_add ? (use_r ? 3 : 2) : -1;          // staged planes: gout, y, (r), (gr_add)
+  const int stage_f = ((use_r ? 3 : 2) + (has_add ? 1 : 0)) * U * TV, iters = (cnt + U - 1) / U;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
   float* sho = sh + 2 * stage_f;                       // gr hand-over, each plane in gr's memory order
   const int gr_mode = has_gr ? plane_mode(q.gr, T, V) : 0;
@@ -721,10 +726,12 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
       stage_async_b<NJ, U, true>(ps, q.gout, c, n, left, d, T, V);
       stage_async_b<NJ, U, true>(ps, q.y, c, n, left, d + du, T, V);
       if (use_r) stage_async_b<NJ, U, true>(ps, q.r, c, n, left, d + 2 * du, T, V);
+      if (has_add) stage_async_b<NJ, U, true>(ps, q.gadd, c, n, left, d + add_region * du, T, V);
     } else {
       stage_async_b<NJ, U, false>(ps, q.gout, c, n, left, d, T, V);
       stage_async_b<NJ, U, false>(ps, q.y, c, n, left, d + du, T, V);
       if (use_r) stage_async_b<NJ, U, false>(ps, q.r, c, n, left, d + 2 * du, T, V);
+      if (has_add) stage_async_b<NJ, U, false>(ps, q.gadd, c, n, left, d + add_region * du, T, V);
     }
   };
   if (iters > 0) issue(0);
@@ -748,15 +755,16 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
   // per position: xhat = (y - mu) * is;  gy = gi * (gp - k1 - xhat * k2)
   float mu[NJ], is[NJ], g[NJ], b[NJ], gi[NJ], k1[NJ], k2[NJ];
   float* gyp[NJ];
-  int sg[NJ], sy[NJ], sr[NJ], so[NJ], me[NJ];
+  int sg[NJ], sy[NJ], sr[NJ], so[NJ], sa[NJ], me[NJ];
   {
-    const bool tfast = t_fastest(q.gy), tf_g = t_fastest(q.gout), tf_y = t_fastest(q.y), tf_r = use_r && t_fastest(q.r);
+    const bool tfast = t_fastest(q.gy), tf_g = t_fastest(q.gout), tf_y = t_fastest(q.y), tf_r = use_r && t_fastest(q.r),
+               tf_a = ADD && t_fastest(q.gadd);
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       mu[i] = is[i] = g[i] = b[i] = gi[i] = k1[i] = k2[i] = 0.f;
       gyp[i] = nullptr;
       sg[i] = -1;
-      sy[i] = sr[i] = so[i] = me[i] = 0;
+      sy[i] = sr[i] = so[i] = sa[i] = me[i] = 0;
       const int pk = tfast ? ps.tf[i] : ps.vf[i];
       if (pk >= 0) {
         const int t = pk >> 8, v = pk & 255;
@@ -775,6 +783,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
         sy[i] = slot_of(tf_y, t, v, T, V);
         sr[i] = slot_of(tf_r, t, v, T, V);
         so[i] = slot_of(tfast_gr, t, v, T, V);
+        if (ADD) sa[i] = slot_of(tf_a, t, v, T, V);
         me[i] = t * V + v;
       }
     }
@@ -787,13 +796,13 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
     const int n = n0 + it * U, left = n1 - n;
     const float* stage = sh + (it & 1) * stage_f;
     if (q.mask)
-      bn_bwd_apply_consume<NJ, U, false, true>(q, stage, sho, gyp, sg, sy, sr, so, me, c, n, left, mu, is, g, b, gi, k1,
+      bn_bwd_apply_consume<NJ, U, false, true, ADD>(q, stage, sho, gyp, sg, sy, sr, so, sa, add_region, me, c, n, left, mu, is, g, b, gi, k1,
                                                k2, slope, has_prelu, use_r, has_gr);
     else if (left >= U)
-      bn_bwd_apply_consume<NJ, U, true, false>(q, stage, sho, gyp, sg, sy, sr, so, me, c, n, left, mu, is, g, b, gi, k1,
+      bn_bwd_apply_consume<NJ, U, true, false, ADD>(q, stage, sho, gyp, sg, sy, sr, so, sa, add_region, me, c, n, left, mu, is, g, b, gi, k1,
                                                k2, slope, has_prelu, use_r, has_gr);
     else
-      bn_bwd_apply_consume<NJ, U, false, false>(q, stage, sho, gyp, sg, sy, sr, so, me, c, n, left, mu, is, g, b, gi,
+      bn_bwd_apply_consume<NJ, U, false, false, ADD>(q, stage, sho, gyp, sg, sy, sr, so, sa, add_region, me, c, n, left, mu, is, g, b, gi,
                                                 k1, k2, slope, has_prelu, use_r, has_gr);
     if (has_gr) {
       __syncthreads();
@@ -829,6 +838,17 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP 
     }
     __syncthreads();
   }
+}
+
+template <int NJ, int U>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_kernel(BnBwdP q) {
+  bn_bwd_apply_body<NJ, U, false>(q);
+}
+// same with a fourth staged tensor, gr_add, summed into gr (separate instantiation: the plain kernel sits at the
+// 64-register cap and pays ~13 % for the extra slots)
+template <int NJ, int U>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_add_kernel(BnBwdP q) {
+  bn_bwd_apply_body<NJ, U, true>(q);
 }
 
 // U (samples per pipeline stage) is a launch-time choice among the compiled instantiations
@@ -935,6 +955,7 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
                    a->ggamma && a->gbeta,
                DSTD_ERR_BAD_ARG, "bn_act_backward: null tensor");
   DSTD_REQUIRE(!a->gr.ptr || a->r.ptr, DSTD_ERR_BAD_ARG, "bn_act_backward: gr requested without r");
+  DSTD_REQUIRE(!a->gr_add.ptr || a->gr.ptr, DSTD_ERR_BAD_ARG, "bn_act_backward: gr_add given without gr");
   DSTD_REQUIRE(a->T * a->V <= BN_MAXJ * BN_THREADS_MAX && a->V <= 32, DSTD_ERR_UNSUPPORTED,
                "bn_act: T*V=%d or V=%d outside the compiled limits", a->T * a->V, a->V);
   DSTD_REQUIRE(a->ws_bytes >= dstd_bn_act_workspace_bytes(a->N, a->C, a->T, a->V) && a->ws, DSTD_ERR_WORKSPACE,
@@ -944,7 +965,7 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   q.N = a->N; q.C = a->C; q.T = a->T; q.V = a->V;
   q.vc_order = a->vc_order; q.training = a->training;
   q.S = bn_act_splits(a->N, a->C);
-  q.y = mk(a->y); q.r = mk(a->r); q.gout = mk(a->gout); q.gy = mk(a->gy); q.gr = mk(a->gr);
+  q.y = mk(a->y); q.r = mk(a->r); q.gout = mk(a->gout); q.gy = mk(a->gy); q.gr = mk(a->gr); q.gadd = mk(a->gr_add);
   q.gamma = a->gamma; q.beta = a->beta; q.prelu = a->prelu; q.mask = a->mask;
   q.save_mean = a->save_mean; q.save_invstd = a->save_invstd;
   q.ggamma = a->ggamma; q.gbeta = a->gbeta; q.gprelu = a->prelu ? a->gprelu : nullptr;
@@ -960,7 +981,13 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   DSTD_BN_DISPATCH_U(bn_bwd_reduce_kernel, g.nj, ub, dim3(q.C, q.S), g.threads, sm_red, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_reduce");
-  DSTD_BN_DISPATCH_U(bn_bwd_apply_kernel, g.nj, ub, dim3(q.C, q.S), g.threads, (size_t)(2 * nst + 1) * ub * tv, st, q);
+  const int nst2 = nst + (q.gadd.p ? 1 : 0);           // pass 2 also stages gr_add
+  const int ub2 = bn_pick_u(tv, 2 * nst2 + 1, ub, BN_SMEM_BUDGET);
+  if (q.gadd.p) {
+    DSTD_BN_DISPATCH_U(bn_bwd_apply_add_kernel, g.nj, ub2, dim3(q.C, q.S), g.threads, (size_t)(2 * nst2 + 1) * ub2 * tv, st, q);
+  } else {
+    DSTD_BN_DISPATCH_U(bn_bwd_apply_kernel, g.nj, ub2, dim3(q.C, q.S), g.threads, (size_t)(2 * nst2 + 1) * ub2 * tv, st, q);
+  }
   count_launch();
   DSTD_LAUNCH_CHECK("bn_bwd_apply");
   return DSTD_OK;

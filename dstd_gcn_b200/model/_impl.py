@@ -188,7 +188,13 @@ class _DSTDGCBBase(nn.Module):
             w_s, r_s = self.W_s.unbind(0), self.R_s.unbind(0)
             brs = [g.branch(a_s[i], w_s[i], r_s[i]) for i, g in enumerate(self.conv_s)]
         y = ops.gc_unit(x4, self.alpha_sm, brs, adj_t=fast)
-        x2 = ops.bn_act(y, self.bn.bn, r=r, prelu=self.prelu.weight, vc_order=fast, out_order=ops.ORDER_V_MAJOR)
+        if ops.FUSE_SKIP_GRAD and skip4 is not None and skip4 is r:
+            # the block input is both the BN residual and the layer skip: route the skip through the BN node so that
+            # the two gradients are summed inside the BN backward kernel
+            x2, skip4 = ops.bn_act(y, self.bn.bn, r=r, prelu=self.prelu.weight, vc_order=fast,
+                                   out_order=ops.ORDER_V_MAJOR, pass_r=True)
+        else:
+            x2 = ops.bn_act(y, self.bn.bn, r=r, prelu=self.prelu.weight, vc_order=fast, out_order=ops.ORDER_V_MAJOR)
         a_t, r_t = self.A_t.unbind(0), self.R_t.unbind(0)
         brt = [g.branch(a_t[i], None, r_t[i]) for i, g in enumerate(self.conv_t)]
         skip_u = None if skip4 is None else skip4.permute(0, 1, 3, 2)

@@ -95,15 +95,15 @@ def _(y, r, gamma, beta, running_mean, running_var, nbt, prelu, mask, out_order,
 @torch.library.custom_op("dstd_b200::bn_act_bwd", mutates_args=())
 def bn_act_bwd(y: Tensor, r: Optional[Tensor], gout: Tensor, gamma: Tensor, beta: Tensor, prelu: Optional[Tensor],
                mask: Optional[Tensor], save_mean: Tensor, save_invstd: Tensor, vc_order: bool, training: bool,
-               need_gr: bool) -> List[Tensor]:
-    """[gy, gr|empty, ggamma, gbeta, gprelu|empty]"""
+               need_gr: bool, gr_add: Optional[Tensor] = None) -> List[Tensor]:
+    """[gy, gr (+ gr_add)|empty, ggamma, gbeta, gprelu|empty]"""
     gy, gr, gg, gb, gp = _lib.backend().bn_act_backward(y, r, gout, gamma, beta, prelu, mask, save_mean, save_invstd,
-                                                        vc_order, training, need_gr)
+                                                        vc_order, training, need_gr, gr_add)
     return [gy, gr if gr is not None else y.new_empty((0,)), gg, gb, gp if gp is not None else y.new_empty((0,))]
 
 
 @bn_act_bwd.register_fake
-def _(y, r, gout, gamma, beta, prelu, mask, save_mean, save_invstd, vc_order, training, need_gr):
+def _(y, r, gout, gamma, beta, prelu, mask, save_mean, save_invstd, vc_order, training, need_gr, gr_add=None):
     return [torch.empty_like(y), torch.empty_like(r) if (r is not None and need_gr) else y.new_empty((0,)),
             torch.empty_like(gamma), torch.empty_like(gamma), y.new_empty((1,) if prelu is not None else (0,))]
 
@@ -235,31 +235,44 @@ def gc_unit(xu: Tensor, alpha: Optional[Tensor], branches: Sequence[dict], skip_
     return _GcUnit.apply(xu, alpha, skip_u, len(branches), adj_t, *flat)
 
 
+# Route the layer skip through the BN node (bn_act(pass_r=True)) so that its gradient is summed inside the BN backward
+# kernel (dstd_bn_act_bwd_args.gr_add).  Off by default: on B200 the fused pass measured 0.3 ms/step slower than the
+# separate strided add it removes (the extra staged tensor costs the BN backward its second CTA-level overlap).
+FUSE_SKIP_GRAD = False
+
+
 class _BnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, r, gamma, beta, prelu, running_mean, running_var, nbt, mask, out_order, vc_order, training,
-                eps, momentum):
+                eps, momentum, pass_r):
         out, mean, invstd = torch.ops.dstd_b200.bn_act_fwd(y, r, gamma, beta, running_mean, running_var, nbt, prelu,
                                                            mask, out_order, vc_order, training, eps, momentum)
         ctx.save_for_backward(y, r, gamma, beta, prelu, mask, mean, invstd)
-        ctx.vc_order, ctx.training = vc_order, training
+        ctx.vc_order, ctx.training, ctx.pass_r = vc_order, training, pass_r
+        if pass_r:
+            # second output = r itself: whatever else consumes r downstream (the layer skip) sends its gradient back
+            # through this node, where the backward kernel adds it to d(pre-activation) in the same pass
+            return out, r.view_as(r)
         return out
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, g_thru=None):
         y, r, gamma, beta, prelu, mask, mean, invstd = ctx.saved_tensors
         need_gr = r is not None and ctx.needs_input_grad[1]
         gy, gr, gg, gb, gp = torch.ops.dstd_b200.bn_act_bwd(y, r, gout, gamma, beta, prelu, mask, mean, invstd,
-                                                            ctx.vc_order, ctx.training, need_gr)
-        return (gy, _opt(gr), gg, gb, _opt(gp), None, None, None, None, None, None, None, None, None)
+                                                            ctx.vc_order, ctx.training, need_gr,
+                                                            g_thru if need_gr else None)
+        return (gy, _opt(gr), gg, gb, _opt(gp), None, None, None, None, None, None, None, None, None, None)
 
 
 def bn_act(y, bn: torch.nn.BatchNorm1d, r=None, prelu=None, mask=None, vc_order=False, out_order=ORDER_LIKE_INPUT,
-           training=None):
+           training=None, pass_r=False):
     """out = mask * prelu(BN(y) + r) on logical [N,C,T,V] tensors of any strides (BN over (N,T) per (c,v)).
 
-    ``out_order``: memory order of the result (lets the op transpose T/V for free)."""
+    ``out_order``: memory order of the result (lets the op transpose T/V for free).
+    ``pass_r``: also return ``r`` (as a second output of the same autograd node); use that alias for every other
+    consumer of ``r`` and the gradients meet inside the BN backward kernel instead of in a separate add."""
     training = bn.training if training is None else training
     use_batch = training or bn.running_mean is None
     mom = 0.0 if bn.momentum is None else bn.momentum
@@ -268,7 +281,7 @@ def bn_act(y, bn: torch.nn.BatchNorm1d, r=None, prelu=None, mask=None, vc_order=
                         bn.running_mean if (track or not use_batch) else None,
                         bn.running_var if (track or not use_batch) else None,
                         bn.num_batches_tracked if track else None,
-                        mask, out_order, vc_order, use_batch, bn.eps, mom)
+                        mask, out_order, vc_order, use_batch, bn.eps, mom, bool(pass_r and r is not None))
 
 
 class _ChMix(torch.autograd.Function):

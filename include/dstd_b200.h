@@ -165,6 +165,10 @@ typedef struct {
   float* gprelu;               /* [1], written when prelu != NULL and ptr != NULL */
   void* ws;
   size_t ws_bytes;
+  dstd_view gr_add;            /* optional (ptr may be NULL; requires gr): gr = d(pre-activation) + gr_add.  Lets the
+                                  caller fold another gradient of the same tensor into this pass -- in DSTDGCB the
+                                  block input is both the BN residual (model/dstdgcn.py:153) and the layer skip
+                                  (:248), and autograd would otherwise sum the two with a separate strided add */
 } dstd_bn_act_bwd_args;
 
 size_t dstd_bn_act_workspace_bytes(int N, int C, int T, int V);

@@ -160,7 +160,7 @@ class EmulBackend:
         return out, self._bn_unindex(mean, vc_order), self._bn_unindex(invstd, vc_order)
 
     def bn_act_backward(self, y, r, gout, gamma, beta, prelu, mask, save_mean, save_invstd, vc_order, training,
-                        need_gr=True):
+                        need_gr=True, gr_add=None):
         n, c, t, v = y.shape
         mean = self._bn_index(save_mean, c, v, vc_order)
         invstd = self._bn_index(save_invstd, c, v, vc_order)
@@ -188,7 +188,7 @@ class EmulBackend:
         gro = None
         if r is not None and need_gr:
             gro = torch.empty_like(r)
-            gro.copy_(gpre)
+            gro.copy_(gpre if gr_add is None else gpre + gr_add)
         return gyo, gro, self._bn_unindex(ggamma, vc_order), self._bn_unindex(gbeta, vc_order), gprelu
 
     # ------------------------------------------------------------------ 1x1 channel mix

@@ -194,6 +194,16 @@ def test_bn_act_abi(case):
             continue
         assert a.shape == b.shape, nm
         assert max_abs(a, b) < 1e-4 * max(1.0, float(b.abs().max())), nm
+    if r is not None:
+        # gr_add: another gradient of r (kept in the OUTPUT's memory order, like the layer-skip gradient) summed into
+        # gr by the same kernel; everything else must be unchanged
+        gadd = torch.empty_strided(out_r.shape, out_r.stride(), dtype=torch.float64)
+        gadd.copy_(rnd(tuple(out_r.shape), g))
+        res2 = be.bn_act_backward(yd, rd, to_dev(gout), gd, bd, pd_, md, mean, istd, vc, training, True, to_dev(gadd))
+        torch.cuda.synchronize()
+        assert max_abs(res2[1], res_r[1] + gadd) < 1e-4 * max(1.0, float(res_r[1].abs().max()))
+        assert res2[1].stride() == res[1].stride()
+        assert torch.equal(res2[0], res[0]) and torch.equal(res2[2], res[2]) and torch.equal(res2[3], res[3])
 
 
 def test_bn_act_large_mean_is_stable():

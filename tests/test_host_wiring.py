@@ -101,6 +101,14 @@ def test_model_module(name, v, layout):
         assert rel_err(m(z["x"]), z["y_eval"]) < 1e-9
 
 
+def test_model_module_with_fused_skip_gradient(monkeypatch):
+    """ops.FUSE_SKIP_GRAD routes the layer skip through the BN node (gr_add of the BN backward): same goldens."""
+    from dstd_gcn_b200 import ops
+    monkeypatch.setattr(ops, "FUSE_SKIP_GRAD", True)
+    test_model_module("std_h36m", 22, "h36m")
+    test_model_module("fast_h36m", 22, "h36m")
+
+
 @pytest.mark.parametrize("variant", ["std", "fast"])
 def test_init_rng_parity_and_appendix_d_anchor(variant):
     """Constructing OUR module under the reference's seed consumes the RNG identically, so the Appendix-D recipe

@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--gr-add", action="store_true", help="backward with a gr_add tensor (layer-skip gradient)")
     a = ap.parse_args()
     dev, be = torch.device("cuda"), _lib.backend()
     n, c, t, v = a.n, 64, 35, 22
@@ -33,14 +34,15 @@ def main():
         ol = _out_like(y, order)
         out, mean, istd = be.bn_act_forward(y, r, gamma, beta, rm, rv, nbt, prelu, None, False, True, 1e-5, 0.1, ol)
         gout = out    # any tensor with the output's layout
-        be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True)
+        gadd = torch.randn_like(gout) if (a.gr_add and r is not None) else None
+        be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True, gadd)
         torch.cuda.synchronize()
         # device time without host gaps: replay each direction as a CUDA graph
         gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(gf):
             be.bn_act_forward(y, r, gamma, beta, rm, rv, nbt, prelu, None, False, True, 1e-5, 0.1, ol)
         with torch.cuda.graph(gb):
-            be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True)
+            be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, True, True, gadd)
         res = []
         for gr in (gf, gb):
             gr.replay()
