@@ -101,10 +101,12 @@ def test_model_module(name, v, layout):
         assert rel_err(m(z["x"]), z["y_eval"]) < 1e-9
 
 
-def test_model_module_with_fused_skip_gradient(monkeypatch):
-    """ops.FUSE_SKIP_GRAD routes the layer skip through the BN node (gr_add of the BN backward): same goldens."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_model_module_skip_gradient_paths(monkeypatch, fused):
+    """ops.FUSE_SKIP_GRAD routes the layer skip through the BN node (gr_add of the BN backward); off = plain autograd
+    sum.  Both reproduce the reference goldens."""
     from dstd_gcn_b200 import ops
-    monkeypatch.setattr(ops, "FUSE_SKIP_GRAD", True)
+    monkeypatch.setattr(ops, "FUSE_SKIP_GRAD", fused)
     test_model_module("std_h36m", 22, "h36m")
     test_model_module("fast_h36m", 22, "h36m")
 
