@@ -50,7 +50,7 @@ class GcBwdArgs(C.Structure):
                 ("br", Branch * MAX_BRANCH),
                 ("m", C.c_void_p), ("pd", C.c_void_p), ("xa", C.c_void_p),
                 ("gbr", BranchGrad * MAX_BRANCH), ("galpha", C.c_void_p),
-                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t), ("gx_add", View)]
 
 
 class BnFwdArgs(C.Structure):
@@ -237,7 +237,7 @@ class CudaBackend:
         self._ok(self.lib.dstd_gc_forward(C.byref(a), _stream()), "dstd_gc_forward")
         return out, m, pd, xa
 
-    def gc_backward(self, xu, gout_u, alpha, brs, m, pd, xa, adj_t, need_galpha=True):
+    def gc_backward(self, xu, gout_u, alpha, brs, m, pd, xa, adj_t, need_galpha=True, gx_add=None):
         n, cin, p_, k_ = xu.shape
         nb = len(brs)
         cout = brs[0]["w_f"].shape[0]
@@ -249,6 +249,7 @@ class CudaBackend:
         a.N, a.Cin, a.Cout, a.P, a.K, a.nb = n, cin, cout, p_, k_, nb
         a.flags = FLAG_ADJ_T if adj_t else 0
         a.x, a.gout, a.gx = _view(xu, "x"), _view(gout_u, "gout"), _view(gx, "gx")
+        a.gx_add = _view(gx_add, "gx_add")
         a.alpha = _cptr(alpha, "alpha")
         self._fill_branches(a.br, brs)
         a.m, a.pd, a.xa = _cptr(m, "m"), _cptr(pd, "pd"), (_cptr(xa, "xa") if xa is not None and xa.numel() else None)

@@ -309,10 +309,11 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   if (mproj_bwd_supported(Cin, 4 * nb)) {
     MprojBwdParams mp;
     mp.Cin = Cin; mp.J = 4 * nb; mp.P = P; mp.K = K; mp.G = G;
-    mp.x = mk(a->x); mp.gx = mk(a->gx); mp.gm = gm; mp.wm = wm; mp.partial = p_wm;
+    mp.x = mk(a->x); mp.gx = mk(a->gx); mp.gx_add = mk(a->gx_add); mp.gm = gm; mp.wm = wm; mp.partial = p_wm;
     if ((rc = launch_mproj_bwd(mp, st))) return rc;
     S1b = mproj_bwd_ctas(G);
   } else {
+    DSTD_REQUIRE(!a->gx_add.ptr, DSTD_ERR_UNSUPPORTED, "gc_backward: gx_add needs the fused m-projection backward (Cin <= 320)");
     BgemmParams g2;
     g2.M = Cin; g2.Kd = 4 * nb; g2.G = G; g2.P = P; g2.K = K;
     g2.w = wm; g2.wsc = C1; g2.wsi = 1; g2.bias = nullptr;

@@ -332,13 +332,14 @@ __global__ void __launch_bounds__(256, 2) mproj_bwd_kernel(MprojBwdParams q) {
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long g = tile * MP_TP + tid;
     const bool ok = g < q.G;
-    long long ox = 0, og = 0, om = 0;
+    long long ox = 0, og = 0, om = 0, oa = 0;
     if (ok) {
       const int n = (int)(g / PK);
       const int rem = (int)(g - (long long)n * PK);
       const int p = rem / q.K, k = rem - p * q.K;
       ox = vix(q.x, n, 0, p, k);
       og = vix(q.gx, n, 0, p, k);
+      if (q.gx_add.p) oa = vix(q.gx_add, n, 0, p, k);
       om = (long long)n * J * PK + rem;
     }
     float gm[8];
@@ -354,6 +355,11 @@ __global__ void __launch_bounds__(256, 2) mproj_bwd_kernel(MprojBwdParams q) {
       float gv[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) gv[u] = (ok && c0 + u < Cin) ? q.gx.p[og + (long long)(c0 + u) * q.gx.sc] : 0.f;
+      if (q.gx_add.p) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (ok && c0 + u < Cin) gv[u] += __ldg(q.gx_add.p + oa + (long long)(c0 + u) * q.gx_add.sc);
+      }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         if (c0 + u < Cin) {

@@ -41,6 +41,7 @@ struct MprojBwdParams {
   long long G;         // columns = N*P*K
   View4 x;             // [N,Cin,P,K]
   View4 gx;            // [N,Cin,P,K] read-modify-write
+  View4 gx_add;        // optional: added into gx in the same pass
   const float* gm;     // dense [N,J,P,K]
   const float* wm;     // [J][Cin+1]
   float* partial;      // [ctas][J][Cin+1]

@@ -187,7 +187,15 @@ class _DSTDGCBBase(nn.Module):
         else:
             w_s, r_s = self.W_s.unbind(0), self.R_s.unbind(0)
             brs = [g.branch(a_s[i], w_s[i], r_s[i]) for i, g in enumerate(self.conv_s)]
-        y = ops.gc_unit(x4, self.alpha_sm, brs, adj_t=fast)
+        if ops.FUSE_SKIP_GRAD and ops.FUSE_RES_GRAD and r is x4:
+            # chain the consumers of the block input (see ops.FUSE_SKIP_GRAD): the residual reads the alias returned by
+            # the spatial unit's node
+            same_skip = skip4 is x4
+            y, r = ops.gc_unit(x4, self.alpha_sm, brs, adj_t=fast, pass_x=True)
+            if same_skip:
+                skip4 = r
+        else:
+            y = ops.gc_unit(x4, self.alpha_sm, brs, adj_t=fast)
         if ops.FUSE_SKIP_GRAD and skip4 is not None and skip4 is r:
             # the block input is both the BN residual and the layer skip: route the skip through the BN node so that
             # the two gradients are summed inside the BN backward kernel

@@ -60,10 +60,11 @@ def _(x, alpha, br, skip, nb, adj_t):
 
 @torch.library.custom_op("dstd_b200::gc_bwd", mutates_args=())
 def gc_bwd(x: Tensor, gout: Tensor, alpha: Optional[Tensor], br: Sequence[Optional[Tensor]], m: Tensor, pd: Tensor,
-           xa: Tensor, nb: int, adj_t: bool) -> List[Tensor]:
-    """Returns [gx, galpha, then per branch: 8 weight grads, adj_eff grad, adj_w grad]; unused slots are 0-size."""
+           xa: Tensor, nb: int, adj_t: bool, gx_add: Optional[Tensor] = None) -> List[Tensor]:
+    """Returns [gx (+ gx_add), galpha, then per branch: 8 weight grads, adj_eff grad, adj_w grad]; unused slots are
+    0-size."""
     brs = _unflatten(br, nb)
-    gx, galpha, grads = _lib.backend().gc_backward(x, gout, alpha, brs, m, pd, xa, adj_t)
+    gx, galpha, grads = _lib.backend().gc_backward(x, gout, alpha, brs, m, pd, xa, adj_t, True, gx_add)
     out = [gx, galpha if galpha is not None else x.new_empty((0,))]
     for g in grads:
         out += [g[k] for k in _GR_KEYS] + [g["adj_eff"], g["adj_w"] if g["adj_w"] is not None else x.new_empty((0,))]
@@ -71,7 +72,7 @@ def gc_bwd(x: Tensor, gout: Tensor, alpha: Optional[Tensor], br: Sequence[Option
 
 
 @gc_bwd.register_fake
-def _(x, gout, alpha, br, m, pd, xa, nb, adj_t):
+def _(x, gout, alpha, br, m, pd, xa, nb, adj_t, gx_add=None):
     k = x.shape[3]
     out = [torch.empty_like(x), x.new_empty((1,) if alpha is not None else (0,))]
     for b in range(nb):
@@ -202,18 +203,22 @@ class _GcUnit(torch.autograd.Function):
     """Sum of `nb` DSTD-GC branches on unit coordinates [N,C,P,K] (+ optional skip)."""
 
     @staticmethod
-    def forward(ctx, x, alpha, skip, nb, adj_t, *flat):
+    def forward(ctx, x, alpha, skip, nb, adj_t, pass_x, *flat):
         out, m, pd, xa = torch.ops.dstd_b200.gc_fwd(x, alpha, list(flat), skip, nb, adj_t)
         ctx.save_for_backward(x, alpha, m, pd, xa, *flat)
         ctx.nb, ctx.adj_t = nb, adj_t
         ctx.has_skip = skip is not None
+        if pass_x:
+            # second output = x itself: other consumers of x (the BN residual) use this alias, so their gradient comes
+            # back through this node and is added by the kernel that writes gx (dstd_gc_bwd_args.gx_add)
+            return out, x.view_as(x)
         return out
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, g_thru=None):
         x, alpha, m, pd, xa, *flat = ctx.saved_tensors
         nb = ctx.nb
-        res = torch.ops.dstd_b200.gc_bwd(x, gout, alpha, list(flat), m, pd, xa, nb, ctx.adj_t)
+        res = torch.ops.dstd_b200.gc_bwd(x, gout, alpha, list(flat), m, pd, xa, nb, ctx.adj_t, g_thru)
         gx, galpha = res[0], _opt(res[1])
         gflat = []
         for b in range(nb):
@@ -221,26 +226,33 @@ class _GcUnit(torch.autograd.Function):
             adj, adj_w, adj_r = flat[b * _NBK + 8], flat[b * _NBK + 9], flat[b * _NBK + 10]
             geff, gadjw = g[8], _opt(g[9])
             gadj = None
-            if ctx.needs_input_grad[5 + b * _NBK + 8]:
+            if ctx.needs_input_grad[6 + b * _NBK + 8]:
                 gadj = geff if adj_w is None else geff * adj_w
             gflat += list(g[:8]) + [gadj, gadjw if adj_w is not None else None, geff if adj_r is not None else None]
-        return (gx, galpha, gout if ctx.has_skip else None, None, None, *gflat)
+        return (gx, galpha, gout if ctx.has_skip else None, None, None, None, *gflat)
 
 
 def gc_unit(xu: Tensor, alpha: Optional[Tensor], branches: Sequence[dict], skip_u: Optional[Tensor] = None,
-            adj_t: bool = False) -> Tensor:
+            adj_t: bool = False, pass_x: bool = False):
     """DSTD-GC unit.  ``xu``: [N,Cin,P,K] (any strides).  ``branches``: dicts with the keys of ``_BR_KEYS``
-    (``adj_w``/``adj_r`` may be None/missing).  Returns [N,Cout,P,K] in the same memory order as ``xu``."""
+    (``adj_w``/``adj_r`` may be None/missing).  Returns [N,Cout,P,K] in the same memory order as ``xu``.
+    ``pass_x``: also return ``xu`` as a second output of the same autograd node (see ``FUSE_SKIP_GRAD``)."""
     flat = []
     for br in branches:
         flat += [br.get(k) for k in _BR_KEYS]
-    return _GcUnit.apply(xu, alpha, skip_u, len(branches), adj_t, *flat)
+    return _GcUnit.apply(xu, alpha, skip_u, len(branches), adj_t, bool(pass_x), *flat)
 
 
-# Route the layer skip through the BN node (bn_act(pass_r=True)) so that its gradient is summed inside the BN backward
-# kernel (dstd_bn_act_bwd_args.gr_add) instead of by a separate strided add: +2.2 % training throughput on B200
-# (same-box A/B).  DSTD_FUSE_SKIP_GRAD=0 restores the plain autograd sum.
+# The block input h feeds the spatial unit, the BN residual and the layer skip; autograd would sum the three gradients
+# with two strided adds per block.  Instead the consumers are chained through pass-through outputs (h -> gc_unit
+# (pass_x) -> bn_act residual (pass_r) -> skip), so the skip gradient is added inside the BN backward kernel
+# (dstd_bn_act_bwd_args.gr_add) and the residual gradient inside the kernel that writes gx
+# (dstd_gc_bwd_args.gx_add).  DSTD_FUSE_SKIP_GRAD=0 restores the plain autograd sums.
 FUSE_SKIP_GRAD = os.environ.get("DSTD_FUSE_SKIP_GRAD", "1") not in ("", "0")
+# the gx_add half of the chain is OFF by default: same-box A/B on B200 gave 9.30-9.43 k samples/s without any fusion,
+# 9.53-9.59 k with the skip half only and 9.41-9.52 k with both (the extra read in the m-projection backward costs
+# more than the strided add it removes)
+FUSE_RES_GRAD = os.environ.get("DSTD_FUSE_RES_GRAD", "0") not in ("", "0")
 
 
 class _BnAct(torch.autograd.Function):

@@ -110,6 +110,9 @@ typedef struct {
   float* galpha;         /* [1], written; NULL => not wanted */
   void* ws;              /* dstd_gc_bwd_workspace_bytes() */
   size_t ws_bytes;
+  dstd_view gx_add;      /* optional (ptr may be NULL): gx = d(out)/d(x)^T gout + gx_add, i.e. another gradient of x
+                            (in DSTDGCB the block input also feeds the BN residual, model/dstdgcn.py:145,153) summed
+                            in the pass that writes gx instead of by a separate add */
 } dstd_gc_bwd_args;
 
 /* 1 when dstd_gc_backward for this shape reads the saved `xa` (unfused fallback); 0 when the fused backward recomputes

@@ -77,12 +77,14 @@ class EmulBackend:
         res.copy_(out)
         return res, m, pd, xa
 
-    def gc_backward(self, xu, gout_u, alpha, brs, m, pd, xa, adj_t, need_galpha=True):
+    def gc_backward(self, xu, gout_u, alpha, brs, m, pd, xa, adj_t, need_galpha=True, gx_add=None):
         n, cin, p_, k_ = xu.shape
         cout = brs[0]["w_f"].shape[0]
         al = 1.0 if alpha is None else alpha.reshape(())
         xaug = torch.cat((xu, xu.new_ones((n, 1, p_, k_))), dim=1)
         gx = torch.zeros_like(xu)
+        if gx_add is not None:
+            gx += gx_add
         galpha = xu.new_zeros((1,))
         grads = []
         for b, br in enumerate(brs):

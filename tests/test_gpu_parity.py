@@ -109,6 +109,14 @@ def test_gc_unit_abi(case):
                 continue
             assert gr[b][key].shape == ref.shape, key
             assert max_abs(gr[b][key], ref) < 1e-4 * max(1.0, float(ref.abs().max())), (b, key)
+    if cin <= 64 and cout <= 64:
+        # gx_add: another gradient of x summed by the kernel that writes gx; nothing else changes
+        gadd = unit_input(g, n, cin, p, k, layout)
+        gx2, ga2, gr2 = be.gc_backward(xd, to_dev(gout), ad, bd, m, pd, xa, adj_t, True, to_dev(gadd))
+        torch.cuda.synchronize()
+        assert gx2.stride() == gx.stride()
+        assert max_abs(gx2, gx.double().cpu() + gadd) < 1e-5 * max(1.0, float(gx_r.abs().max()))
+        assert torch.equal(ga2, ga) and all(torch.equal(gr2[b]["w_f"], gr[b]["w_f"]) for b in range(nb))
 
 
 @pytest.mark.parametrize("case", [GC_CASES[2], GC_CASES[3], GC_CASES[6]], ids=["enc_spatial", "temporal_skip", "fast"])

@@ -101,12 +101,13 @@ def test_model_module(name, v, layout):
         assert rel_err(m(z["x"]), z["y_eval"]) < 1e-9
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [(True, True), (True, False), (False, False)])
 def test_model_module_skip_gradient_paths(monkeypatch, fused):
-    """ops.FUSE_SKIP_GRAD routes the layer skip through the BN node (gr_add of the BN backward); off = plain autograd
-    sum.  Both reproduce the reference goldens."""
+    """ops.FUSE_SKIP_GRAD routes the layer skip through the BN node (gr_add of the BN backward), ops.FUSE_RES_GRAD also
+    the BN residual through the spatial unit's node (gx_add); off = plain autograd sums.  All reproduce the goldens."""
     from dstd_gcn_b200 import ops
-    monkeypatch.setattr(ops, "FUSE_SKIP_GRAD", fused)
+    monkeypatch.setattr(ops, "FUSE_SKIP_GRAD", fused[0])
+    monkeypatch.setattr(ops, "FUSE_RES_GRAD", fused[1])
     test_model_module("std_h36m", 22, "h36m")
     test_model_module("fast_h36m", 22, "h36m")
 
