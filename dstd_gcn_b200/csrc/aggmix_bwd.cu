@@ -339,13 +339,13 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
         }
       }
       if (tid < Cout) {   // bias gradient: sum_pos gout[o][pos] * (column sums of xmu)
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four independent chains (the loop is latency bound)
         for (int p4 = 0; p4 < npos_pad; p4 += 4) {
           const float4 a = *reinterpret_cast<const float4*>(gos + tid * LD + p4);
           const float4 c = *reinterpret_cast<const float4*>(xas + Cin * LD + p4);
-          s = fmaf(a.x, c.x, s); s = fmaf(a.y, c.y, s); s = fmaf(a.z, c.z, s); s = fmaf(a.w, c.w, s);
+          s0 = fmaf(a.x, c.x, s0); s1 = fmaf(a.y, c.y, s1); s2 = fmaf(a.z, c.z, s2); s3 = fmaf(a.w, c.w, s3);
         }
-        accb[b] += s;
+        accb[b] += (s0 + s1) + (s2 + s3);
       }
 
       PH(4);
