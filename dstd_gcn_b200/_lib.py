@@ -111,6 +111,8 @@ SYMBOLS = {
     "dstd_last_error": (C.c_char_p, []),
     "dstd_version": (C.c_char_p, []),
     "dstd_kernel_launch_count": (C.c_int, []),
+    "dstd_device_error": (C.c_int, [C.c_int]),
+    "dstd_debug_raise_device_error": (C.c_int, [C.c_int, C.c_void_p]),
 }
 
 _lib = None

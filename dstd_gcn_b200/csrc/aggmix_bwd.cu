@@ -541,7 +541,7 @@ int aggmix_bwd_ctas(int N, int P, int K, int Cin, int Cout, int nb) {
   AggMixBwdGeom g;
   if (!aggmix_bwd_geom(Cin, Cout, P, K, nb, g)) return 0;
   long long items = (long long)N * ((P + g.PCH - 1) / g.PCH);
-  return (int)(items < 148 ? items : 148);
+  return (int)(items < num_sms() ? items : num_sms());
 }
 // per-CTA weight-gradient partials: two (one per warp group)
 

@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
   }
-  if (!ok && tid == 0) atomicExch(err_flag, 1);
+  if (!ok && tid == 0 && err_flag) {
+    *(volatile int*)err_flag = 1;
+    __threadfence_system();
+  }
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
@@ -326,10 +329,9 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
 // wtc[b][hi|lo][tc_off(o, j)]: conv_f weights (+ bias in K row Cin) of branch b as UMMA K-major core matrices, TF32 split
 // One pass over the padded image (NP output rows x KD reduction rows per branch): out-of-range rows are written as
 // zeros, so no separate clear is needed (the 16-byte gaps between core matrices are never read by the MMA).
-__global__ void pack_tc_kernel(PackParams q, float* wtc, int KD, int NP, int* err_flag) {
+__global__ void pack_tc_kernel(PackParams q, float* wtc, int KD, int NP) {
   const int sbo_f = (KD / 4) * TC_LBO_F, tile = (NP / 8) * sbo_f;
   const int total = q.nb * NP * KD;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *err_flag = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int j = i % KD;
     int t = i / KD;
@@ -394,15 +396,15 @@ int launch_aggmix_fwd_tc(AggMixParams q, const PackParams& pk, float* wtc_ws, cu
   TcGeom g;
   DSTD_REQUIRE(tc_geom(q.Cin, q.Cout, q.P, q.K, q.nb, g, q.skip.p != nullptr), DSTD_ERR_UNSUPPORTED,
                "aggmix_fwd_tc: shape outside limits");
-  int* err_flag = reinterpret_cast<int*>(wtc_ws + g.wtc_floats);
-  pack_tc_kernel<<<min(cdiv(q.nb * g.NP * g.KD, 256), 64), 256, 0, st>>>(pk, wtc_ws, g.KD, g.NP, err_flag);
+  int* err_flag = device_error_word();     // host-mapped: the next entry point reports a timed-out pipeline
+  pack_tc_kernel<<<min(cdiv(q.nb * g.NP * g.KD, 256), 64), 256, 0, st>>>(pk, wtc_ws, g.KD, g.NP);
   count_launch();
   DSTD_LAUNCH_CHECK("pack_tc");
   q.PCH = g.PCH;
   q.CoutP = g.NP;
   q.wtc = wtc_ws;
   const long long items = (long long)q.N * cdiv(q.P, g.PCH);
-  const int ctas = (int)(items < 148 ? items : 148);
+  const int ctas = (int)(items < num_sms() ? items : num_sms());
 #define DSTD_AMTC(WH_)                                                                      \
   if (g.WH == WH_) {                                                                        \
     auto kern = aggmix_fwd_tc_kernel<WH_>;                                                  \

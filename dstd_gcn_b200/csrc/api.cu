@@ -3,8 +3,10 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <set>
+#include <utility>
 
 #include "kernels.cuh"
 
@@ -36,25 +38,88 @@ static int max_dyn_for(const void* kernel) {
   return MAX_DYN_SMEM - (int)fa.sharedSizeBytes;
 }
 
+static int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return d;
+}
+
+int num_sms() {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  const int d = current_device();
+  if (d < 0) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(d);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n < 1) { cudaGetLastError(); n = 148; }
+  cache[d] = n;
+  return n;
+}
+
+// cudaFuncSetAttribute applies to the current device only: remember (device, kernel) pairs
 void ensure_max_smem(const void* kernel) {
   static std::mutex mu;
-  static std::set<const void*> done;
+  static std::set<std::pair<int, const void*>> done;
+  const int d = current_device();
   std::lock_guard<std::mutex> lk(mu);
-  if (done.count(kernel)) return;
+  if (done.count({d, kernel})) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_for(kernel));
-  done.insert(kernel);
+  done.insert({d, kernel});
 }
 
 // Streaming kernels with modest dynamic shared memory: without a preference the driver picks the smallest carve-out
 // that fits ONE CTA (measured: bn_bwd_apply ran 1 CTA/SM), so ask for the largest shared-memory partition once.
 void prefer_smem_carveout(const void* kernel, bool need_max) {
   static std::mutex mu;
-  static std::set<const void*> done;
+  static std::set<std::pair<int, const void*>> done;
+  const int d = current_device();
   std::lock_guard<std::mutex> lk(mu);
-  if (done.count(kernel)) return;
+  if (done.count({d, kernel})) return;
   if (need_max) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_for(kernel));
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  done.insert(kernel);
+  done.insert({d, kernel});
+}
+
+// ---- device-side error word (host-mapped, so that reading it never synchronises)
+static int* g_err_host = nullptr;
+static int* g_err_dev = nullptr;
+static std::mutex g_err_mu;
+
+int* device_error_word() {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  if (g_err_dev) return g_err_dev;
+  int* h = nullptr;
+  if (cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();     // e.g. called for the first time under stream capture: the kernel then runs without the word
+    return nullptr;
+  }
+  *h = 0;
+  int* d = nullptr;
+  if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeHost(h);
+    return nullptr;
+  }
+  g_err_host = h;
+  g_err_dev = d;
+  return g_err_dev;
+}
+
+int poll_device_error(const char* fn) {
+  const int* h = g_err_host;
+  if (h && *(volatile const int*)h != 0) {
+    set_error("%s: an earlier kernel of this library reported a device-side failure (code %d: tensor-core pipeline "
+              "timeout); its outputs are invalid.  dstd_device_error(1) clears the condition", fn, *(volatile const int*)h);
+    return DSTD_ERR_CUDA;
+  }
+  return DSTD_OK;
+}
+
+__global__ void raise_device_error_kernel(int* word, int code) {
+  *(volatile int*)word = code;
+  __threadfence_system();
 }
 
 struct GcWs {
@@ -66,16 +131,20 @@ struct GcWs {
 
 static size_t gc_fwd_ws(int Cin, int Cout, int nb, int P = 40, int K = 40) {
   return arena_need({(size_t)Cout * nb * (Cin + 1) * 4, (size_t)4 * nb * (Cin + 1) * 4,
-                     (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4, aggmix_tc_ws_floats(Cin, Cout, P, K, nb) * 4});
+                     (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4, aggmix_tc_ws_floats(Cin, Cout, P, K, nb) * 4,
+                     unit_tc_ws_bytes(nb)});
 }
+// per-CTA partial slots of the persistent kernels (one or two per SM)
+static size_t part_slots() { return (size_t)2 * num_sms(); }
 static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   const size_t C1 = Cin + 1, G = (size_t)N * P * K;
   const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N, nb);
-  const size_t unf = aggmix_bwd_supported(Cin, Cout, P, K, nb) ? 0 : 1;   // buffers only the unfused path needs
+  const size_t unf = (unit_tc_supported(Cin, Cout, P, K, nb) || aggmix_bwd_supported(Cin, Cout, P, K, nb)) ? 0 : 1;   // buffers only the unfused path needs
+  const size_t ps = part_slots();
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
-                     G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, (size_t)(S1 > 296 ? S1 : 296) * 4 * nb * C1 * 4,
+                     G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, ((size_t)S1 > ps ? (size_t)S1 : ps) * 4 * nb * C1 * 4,
                      (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4,
-                     (size_t)296 * nb * Cout * Cin * 4, (size_t)148 * nb * Cout * 4});
+                     ps * nb * Cout * Cin * 4, ps * nb * Cout * 4, unit_tc_ws_bytes(nb)});
 }
 
 static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const dstd_branch* br, const char* fn) {
@@ -125,8 +194,25 @@ using namespace dstd;
 extern "C" const char* dstd_last_error(void) { return g_err; }
 extern "C" const char* dstd_version(void) { return "dstd_b200 0.1 sm_100a"; }
 extern "C" int dstd_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int dstd_device_error(int clear) {
+  device_error_word();
+  int v = 0;
+  if (g_err_host) {
+    v = *(volatile int*)g_err_host;
+    if (clear) *(volatile int*)g_err_host = 0;
+  }
+  return v;
+}
+extern "C" int dstd_debug_raise_device_error(int code, dstd_stream_t stream) {
+  int* w = device_error_word();
+  DSTD_REQUIRE(w, DSTD_ERR_CUDA, "debug_raise_device_error: the error word is unavailable");
+  raise_device_error_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(w, code);
+  count_launch();
+  return check_launch("raise_device_error");
+}
 
 extern "C" int dstd_gc_needs_xa(int Cin, int Cout, int P, int K, int nb) {
+  if (unit_tc_supported(Cin, Cout, P, K, nb)) return 0;
   return (aggmix_supported(Cin, Cout, P, K, nb) && aggmix_bwd_supported(Cin, Cout, P, K, nb)) ? 0 : 1;
 }
 extern "C" size_t dstd_gc_fwd_workspace_bytes(int N, int Cin, int Cout, int P, int K, int nb) {
@@ -140,7 +226,9 @@ extern "C" size_t dstd_gc_bwd_workspace_bytes(int N, int Cin, int Cout, int P, i
 // ---------------------------------------------------------------------------------------------- DSTD-GC forward
 extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) {
   DSTD_REQUIRE(a, DSTD_ERR_BAD_ARG, "gc_forward: null args");
-  int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_forward");
+  int rc = poll_device_error("gc_forward");
+  if (rc) return rc;
+  rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_forward");
   if (rc) return rc;
   DSTD_REQUIRE(a->x.ptr && a->out.ptr && a->m && a->pd, DSTD_ERR_BAD_ARG, "gc_forward: null tensor");
   DSTD_REQUIRE(a->ws && a->ws_bytes >= gc_fwd_ws(a->Cin, a->Cout, a->nb, a->P, a->K), DSTD_ERR_WORKSPACE,
@@ -153,8 +241,10 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   float* wm = ar.take<float>((size_t)4 * nb * C1);
   float* wcatT = ar.take<float>((size_t)nb * C1 * ((Cout + 7) / 8 * 8));
   float* wtc = ar.take<float>(aggmix_tc_ws_floats(Cin, Cout, P, K, nb));
-  const bool use_tc = !a->xa && aggmix_tc_supported(Cin, Cout, P, K, nb);   // tcgen05 channel mix
-  const bool fused = aggmix_supported(Cin, Cout, P, K, nb);
+  void* wunit = ar.take<char>(unit_tc_ws_bytes(nb));
+  const bool use_unit = !a->xa && unit_tc_supported(Cin, Cout, P, K, nb);    // every contraction on tcgen05 (unit_tc.cu)
+  const bool use_tc = !a->xa && aggmix_tc_supported(Cin, Cout, P, K, nb);   // tcgen05 channel mix only (aggmix_tc.cu)
+  const bool fused = use_unit || aggmix_supported(Cin, Cout, P, K, nb);
 
   PackParams pk;
   fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm, fused ? wcatT : nullptr);
@@ -192,6 +282,7 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
     am.wcatT = wcatT;
     am.wtc = nullptr;
     am.xa = a->xa;
+    if (use_unit) return launch_unit_fwd_tc(am, pk, wunit, st);
     if (use_tc) return launch_aggmix_fwd_tc(am, pk, wtc, st);
     return launch_aggmix_fwd(am, st);
   }
@@ -216,7 +307,9 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
 // ---------------------------------------------------------------------------------------------- DSTD-GC backward
 extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream) {
   DSTD_REQUIRE(a, DSTD_ERR_BAD_ARG, "gc_backward: null args");
-  int rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_backward");
+  int rc = poll_device_error("gc_backward");
+  if (rc) return rc;
+  rc = gc_check_common(a->N, a->Cin, a->Cout, a->P, a->K, a->nb, a->br, "gc_backward");
   if (rc) return rc;
   DSTD_REQUIRE(a->x.ptr && a->gout.ptr && a->gx.ptr && a->m && a->pd, DSTD_ERR_BAD_ARG, "gc_backward: null tensor");
   const int N = a->N, Cin = a->Cin, Cout = a->Cout, P = a->P, K = a->K, nb = a->nb, C1 = Cin + 1;
@@ -229,17 +322,20 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   Arena ar(a->ws, a->ws_bytes);
   float* wcat = ar.take<float>((size_t)Cout * nb * C1);
   float* wm = ar.take<float>((size_t)4 * nb * C1);
-  const bool fused = aggmix_bwd_supported(Cin, Cout, P, K, nb);
+  const bool use_unit = unit_tc_supported(Cin, Cout, P, K, nb);
+  const bool fused = use_unit || aggmix_bwd_supported(Cin, Cout, P, K, nb);
+  const size_t ps = part_slots();
   float* gxa = ar.take<float>(fused ? 0 : (size_t)G * nb * C1);
   float* gxm = ar.take<float>((size_t)G * nb * K);
   float* gm = ar.take<float>((size_t)G * nb * 4);
   float* p_wcat = ar.take<float>(fused ? 0 : (size_t)S1 * Cout * nb * C1);
-  float* p_wm = ar.take<float>((size_t)(S1 > 296 ? S1 : 296) * 4 * nb * C1);
+  float* p_wm = ar.take<float>(((size_t)S1 > ps ? (size_t)S1 : ps) * 4 * nb * C1);
   float* p_wrm = ar.take<float>((size_t)S2 * nb * P * (2 * P + 1));
   float* p_adj = ar.take<float>((size_t)S2 * nb * K * K);
   float* p_alpha = ar.take<float>((size_t)S2 * nb);
-  float* p_wf = ar.take<float>((size_t)296 * nb * Cout * Cin);
-  float* p_bf = ar.take<float>((size_t)148 * nb * Cout);
+  float* p_wf = ar.take<float>(ps * nb * Cout * Cin);
+  float* p_bf = ar.take<float>(ps * nb * Cout);
+  void* wunit = ar.take<char>(unit_tc_ws_bytes(nb));
 
   PackParams pk;
   fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm);
@@ -260,8 +356,13 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
       am.w_f[b] = s.w_f; am.b_f[b] = s.b_f;
     }
     am.gxm = gxm; am.part_w = p_wf; am.part_b = p_bf;
-    if ((rc = launch_aggmix_bwd(am, st))) return rc;
-    n_wf = aggmix_bwd_ctas(N, P, K, Cin, Cout, nb);
+    if (use_unit) {
+      if ((rc = launch_unit_bwd_tc(am, pk, wunit, st))) return rc;
+      n_wf = unit_bwd_tc_ctas(N, Cin, Cout, P, K, nb);
+    } else {
+      if ((rc = launch_aggmix_bwd(am, st))) return rc;
+      n_wf = aggmix_bwd_ctas(N, P, K, Cin, Cout, nb);
+    }
   } else {
   DSTD_REQUIRE(a->xa, DSTD_ERR_BAD_ARG, "gc_backward: the unfused path needs the saved xa buffer");
 

@@ -13,8 +13,13 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> status (+message)
 void prefer_smem_carveout(const void* kernel, bool need_max);  // largest smem carve-out (+227 KB opt-in if need_max)
-void ensure_max_smem(const void* kernel);  // one-time opt-in to 227 KB dynamic shared memory (capture-safe afterwards)
+void ensure_max_smem(const void* kernel);  // one-time (per device) opt-in to 227 KB dynamic shared memory
 constexpr int MAX_DYN_SMEM = 227 * 1024;
+int num_sms();              // multiprocessors of the current device (148 on B200; also the answer when no device is present)
+// Device-side failures (a tensor-core pipeline whose mbarrier wait timed out) are written to one host-mapped word by
+// the kernel and surfaced by the NEXT entry point as DSTD_ERR_CUDA (sticky until dstd_device_error(1) clears it).
+int* device_error_word();   // device pointer to the word (nullptr when it cannot be set up, e.g. under stream capture)
+int poll_device_error(const char* fn);
 
 #define DSTD_REQUIRE(cond, code, ...)      \
   do {                                     \

@@ -259,7 +259,7 @@ bool dynadj_supported(int P, int K) {
 // batch splits = persistent CTAs per branch: one CTA per SM in total (the tensor-path kernel keeps its gWrm tile in
 // registers across its samples, so fewer, longer CTAs amortise the prologue and the partial write-out)
 int dynadj_bwd_splits(int N, int nb) {
-  int s = 148 / (nb < 1 ? 1 : nb);
+  int s = num_sms() / (nb < 1 ? 1 : nb);
   if (s < 1) s = 1;
   return N < s ? N : s;
 }

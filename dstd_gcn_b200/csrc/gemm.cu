@@ -415,7 +415,8 @@ bool mproj_bwd_supported(int Cin, int J) {
 
 int mproj_bwd_ctas(long long G) {
   long long t = (G + MP_TP - 1) / MP_TP;
-  return (int)(t < 296 ? t : 296);
+  const int cap = 2 * num_sms();
+  return (int)(t < cap ? t : cap);
 }
 
 int launch_mproj_bwd(const MprojBwdParams& q, cudaStream_t st) {

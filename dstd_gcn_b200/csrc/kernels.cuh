@@ -168,6 +168,13 @@ int launch_aggmix_bwd(AggMixBwdParams q, cudaStream_t st);
 bool aggmix_bwd_supported(int Cin, int Cout, int P, int K, int nb);
 int aggmix_bwd_ctas(int N, int P, int K, int Cin, int Cout, int nb);
 
+// ------------------------------------------------------------------ unit_tc.cu (all contractions on tcgen05, bf16x3 operands)
+bool unit_tc_supported(int Cin, int Cout, int P, int K, int nb);
+size_t unit_tc_ws_bytes(int nb);
+int unit_bwd_tc_ctas(int N, int Cin, int Cout, int P, int K, int nb);
+int launch_unit_fwd_tc(const AggMixParams& q, const PackParams& pk, void* ws, cudaStream_t st);
+int launch_unit_bwd_tc(const AggMixBwdParams& q, const PackParams& pk, void* ws, cudaStream_t st);
+
 // ------------------------------------------------------------------ bn_act.cu
 int bn_act_splits(int N, int C);
 

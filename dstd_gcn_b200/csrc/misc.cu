@@ -184,7 +184,7 @@ using namespace dstd;
 
 static int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
-  if (b > 148 * 16) b = 148 * 16;
+  if (b > num_sms() * 16) b = num_sms() * 16;
   if (b < 1) b = 1;
   return (int)b;
 }

@@ -82,6 +82,26 @@ class TrainStep:
         self._graph_has_update = False
         self._static = None
         self._static_loss = None
+        if self.world > 1:
+            self.sync_state()
+
+    def sync_state(self, src: int = 0):
+        """Make every rank start from rank `src`'s replica: parameters, Adam moments, step count, learning rate and the
+        model's buffers (BatchNorm running statistics) are broadcast, as DistributedDataParallel does at construction.
+        Without it ranks that were seeded differently, or of which only one loaded a checkpoint, would silently train
+        diverging replicas (the only other collective is the gradient all-reduce).  Called from ``__init__`` and
+        ``load_checkpoint`` when world > 1."""
+        if self.world <= 1:
+            return
+        gsrc = dist.get_global_rank(self.pg, src) if self.pg is not None else src
+        for t in (self.flat.param, self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr_dev):
+            dist.broadcast(t, gsrc, group=self.pg)
+        for p in self.model.parameters():          # frozen parameters (A_s / A_t) live outside the flat bucket
+            if not p.requires_grad:
+                dist.broadcast(p.data, gsrc, group=self.pg)
+        for b in self.model.buffers():
+            dist.broadcast(b, gsrc, group=self.pg)
+        self.lr = float(self.lr_dev.item())
 
     def set_lr(self, lr):
         self.lr = float(lr)
@@ -321,4 +341,6 @@ def load_checkpoint(path_or_state, model, step: Optional["TrainStep"] = None, mo
             nsteps = max(nsteps, int(float(st["step"])))
         step.step_dev.fill_(nsteps)
         step.set_lr(state.get("lr", step.lr))
+    if step is not None and step.world > 1:
+        step.sync_state()                   # every rank continues from rank 0's copy of what was loaded
     return state.get("epoch", 0), state.get("err", float("inf"))

@@ -237,6 +237,12 @@ int dstd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
 const char* dstd_last_error(void);
 const char* dstd_version(void);      /* "dstd_b200 <ver> sm_100a" */
 int dstd_kernel_launch_count(void);  /* kernels launched by this library in this process (monotonic) */
+/* Device-side failures.  A tensor-core pipeline whose completion barrier times out cannot return a status (nothing here
+ * synchronises), so the kernel poisons its outputs with NaN and writes a code into a host-mapped word; every later
+ * dstd_gc_* call then fails with DSTD_ERR_CUDA until the word is cleared.  dstd_device_error returns the word (0 = none)
+ * and clears it when `clear` != 0; dstd_debug_raise_device_error sets it from a kernel on `stream` (test hook). */
+int dstd_device_error(int clear);
+int dstd_debug_raise_device_error(int code, dstd_stream_t stream);
 
 #ifdef __cplusplus
 }

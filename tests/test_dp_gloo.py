@@ -39,10 +39,13 @@ def _worker(rank, world, port, q):
         sd = m.state_dict()
         for k in sd:
             sd[k] = split(z, "p.")[k].clone()
+            if rank != 0 and sd[k].is_floating_point():
+                sd[k] = sd[k] + 0.37        # only rank 0 holds the real weights / running statistics ...
         m.load_state_dict(sd)
         m.train()
-        step = TrainStep(m, lr=3e-3, inverse=True)
-        assert step.world == world
+        step = TrainStep(m, lr=3e-3 if rank == 0 else 1.0, inverse=True)      # ... and the real learning rate:
+        assert step.world == world                                            # TrainStep broadcasts rank 0's state
+        assert abs(step.lr - 3e-3) < 1e-12
         losses = []
         for s in range(2):
             sl = slice(rank * 2, rank * 2 + 2)          # contiguous shard of the 4-sample golden batch
