@@ -8,8 +8,10 @@ poses: forward on the batch, forward on the time-reversed batch (``inverse: True
 losses, one backward, gradient all-reduce (N > 1), Adam.  Under torchrun every rank runs its own shard
 (``--batch`` samples per GPU, weak scaling) and rank 0 prints ONE JSON line.
 
-``--impl reference`` times the reference's CPU implementation of the same step (the oracle port, all host threads)
-on a bounded sample of the workload; it never touches the GPU library.
+``--impl reference`` times the reference's own CPU implementation of the same step -- the UNMODIFIED reference
+(`baseline/_ref`, vendored by ``__graft_entry__.build()``; ``PredictionEngine.train`` around ``DSTDGCN``) on all host
+threads, same workload, batch and dropout as the GPU arm, on a bounded sample; it never touches the GPU library.  The GPU
+arm additionally reports ``gpu_eager_baseline``: the same reference loop with the model on the B200 (torch eager).
 """
 from __future__ import annotations
 
@@ -158,10 +160,64 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# =============================================================================================== CPU reference arm
-def cpu_reference_step_fn(workload, batch, threads):
-    """The reference's CPU path for one engine step (oracle port of engine/prediction.py:215-294 in fp32, torch CPU
-    kernels, all host threads)."""
+# =============================================================================================== reference arms
+class _NullLogger:
+    def info(self, *a, **k):
+        pass
+
+
+def load_reference():
+    """The UNMODIFIED reference hot path + engine loop, vendored by ``__graft_entry__.build()`` into the git-ignored
+    ``baseline/_ref/`` (model/dstdgcn.py, model/layers/*, engine/prediction.py, engine/utils/*).  None if absent."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "engine", "prediction.py")):
+        try:
+            import __graft_entry__ as ge
+            ge.vendor_reference()
+        except Exception:
+            pass
+    if not os.path.exists(os.path.join(ref, "engine", "prediction.py")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import importlib
+    return importlib.import_module("model.dstdgcn"), importlib.import_module("engine.prediction")
+
+
+ENGINE_CFG = {  # configs/dstdgcn/dstdgcn_h36m.yaml:144-160 (the engine section is the same for the three datasets)
+    "learn": {"opt": "adam", "lr": 3e-3, "weight_decay": 0, "gamma": 0.9, "step_size": 5},
+    "loss": {"joint": ["jl2", 1]}, "n_out": 1, "transform": "tsc", "use_weight": False, "inverse": True, "max_iter": 2000}
+
+
+def reference_engine(workload, device):
+    """``PredictionEngine`` of the reference around the reference ``DSTDGCN`` with the workload's constructor arguments
+    (dropout included), exactly as ``runner/base.py:33-37`` assembles them, on `device`."""
+    import torch
+    ref = load_reference()
+    if ref is None:
+        return None
+    ref_model, ref_engine = ref
+    layout, v, t_in, t_out, drop = WORKLOADS[workload]
+    torch.manual_seed(777)
+    m = ref_model.DSTDGCN(6, t_in, t_out, drop, v, C_FEAT, N_LAYERS, layout)
+    for p in m.parameters():            # what `.to("cuda")` does to the A_s / R_s alias (SURVEY.md section 0, quirk 1)
+        p.data = p.data.clone()
+    m = perturb(m).to(device)
+    return ref_engine.PredictionEngine(ENGINE_CFG, m, _NullLogger())
+
+
+def reference_loader(workload, batch, k, seed=777):
+    layout, v, t_in, t_out, _ = WORKLOADS[workload]
+    t = t_in + t_out
+    out = []
+    for i in range(min(k, 4)):
+        a, b, c = synthetic_batch(batch, t, v, t_in, seed=seed + i)
+        out.append((a, b, c, c))
+    return [out[i % len(out)] for i in range(k)]
+
+
+def oracle_step_fn(workload, batch, threads, drop):
+    """Fallback when baseline/_ref is absent: the oracle port of engine/prediction.py:215-294 (fp32, torch CPU)."""
     import torch
     from dstd_gcn_b200.model import dstdgcn as std
     from oracle import dstd_oracle as orc
@@ -186,14 +242,70 @@ def cpu_reference_step_fn(workload, batch, threads):
 
 
 def time_cpu_reference(workload, batch, steps, warmup, threads):
-    step = cpu_reference_step_fn(workload, batch, threads)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    """(samples/s, s/step, kind) of the reference's CPU path: ``PredictionEngine.train`` of the vendored reference, all
+    host threads; the only shim is ``Tensor.cuda`` -> identity (the loop calls ``.cuda()`` on every batch,
+    engine/prediction.py:223-225).  Falls back to the oracle port when baseline/_ref is absent."""
+    import torch
+    torch.set_num_threads(threads)
+    eng = reference_engine(workload, "cpu")
+    if eng is None:
+        step = oracle_step_fn(workload, batch, threads, WORKLOADS[workload][4])
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+        return batch * steps / dt, dt / steps, "port"
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        devnull = open(os.devnull, "w")
+        err, sys.stderr = sys.stderr, devnull          # tqdm progress bars of the reference loop
+        try:
+            if warmup:
+                eng.train(reference_loader(workload, batch, warmup), 0, max_iter=warmup)
+            loader = reference_loader(workload, batch, steps)
+            t0 = time.perf_counter()
+            eng.train(loader, 0, max_iter=steps)
+            dt = time.perf_counter() - t0
+        finally:
+            sys.stderr = err
+            devnull.close()
+    finally:
+        torch.Tensor.cuda = real_cuda
+    return batch * steps / dt, dt / steps, "reference"
+
+
+def time_gpu_eager_reference(workload, batch, steps, warmup):
+    """The same unmodified reference loop with the model on the B200 (torch eager: cuDNN / cuBLAS, TF32 off), the only
+    pre-existing Blackwell path of this workload.  CUDA-event timed around ``train``; includes
+    what the reference does every step: the batch upload and the ``loss.item()`` sync."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    eng = reference_engine(workload, "cuda")
+    if eng is None:
+        return None
+    devnull = open(os.devnull, "w")
+    err, sys.stderr = sys.stderr, devnull
+    try:
+        eng.train(reference_loader(workload, batch, warmup), 0, max_iter=warmup)
+        loader = [tuple(x.pin_memory() for x in b) for b in reference_loader(workload, batch, steps)]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.train(loader, 0, max_iter=steps)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        sys.stderr = err
+        devnull.close()
+    ms = e0.elapsed_time(e1)
+    return {"value": batch * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
+            "what": "unmodified reference (baseline/_ref: model/dstdgcn.py + engine/prediction.py PredictionEngine.train) "
+                    f"on the same B200, torch {torch.__version__} eager fp32 (TF32 off), batch {batch}, same synthetic "
+                    "batches from pinned host memory, loss.item() every step as the reference does"}
 
 
 def run_reference_arm(args):
@@ -201,16 +313,25 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 32                      # the reference's own batch size (configs/dstdgcn/dstdgcn_h36m.yaml)
-    sps, sec = time_cpu_reference(args.workload, batch, args.steps, max(args.warmup, 1), threads)
-    layout, v, t_in, t_out, _ = WORKLOADS[args.workload]
-    sample = f"{args.steps} engine steps of batch {batch} (fp32, two forwards + backward + Adam each), oracle port"
+    warm = max(min(args.warmup, 2), 1)
+    steps = args.steps
+    if args.cpu_seconds > 0:            # bound the CPU work: probe one step, then fit the sample into the budget
+        _, sec1, _ = time_cpu_reference(args.workload, args.batch, 1, 1, threads)
+        steps = max(2, min(args.steps, int(args.cpu_seconds / max(sec1, 1e-3))))
+        warm = 0
+    sps, sec, kind = time_cpu_reference(args.workload, args.batch, steps, warm, threads)
+    sps32, sec32, _ = time_cpu_reference(args.workload, 32, max(2, min(steps, 10)), 1, threads)
+    what = ("unmodified reference (baseline/_ref) PredictionEngine.train" if kind == "reference" else "oracle port")
+    sample = (f"{steps} engine steps of batch {args.batch} (fp32, two forwards + backward + Adam each), {what}, "
+              f"{sec:.2f} s/step")
     line = {
         "impl": "reference", "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, batch_override=batch),
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
+        "batch32": {"value": sps32, "unit": "samples/s", "ms_per_step": sec32 * 1e3,
+                    "note": "the reference's own batch size (configs/dstdgcn/dstdgcn_h36m.yaml), BASELINE.json config 1"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -323,6 +444,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=90.0,
+                    help="--impl reference: budget of CPU work for the timed sample (0 = run exactly --steps)")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -449,13 +573,17 @@ def main():
             line["roofline"]["dominant_call"] = dominant_call_roofline(args.batch, v, t, peak)
         except Exception as e:      # never lose the bench line over the extra measurement
             line["roofline"]["dominant_call"] = {"error": repr(e)}
+        if not args.no_gpu_eager_baseline:
+            try:
+                line["gpu_eager_baseline"] = time_gpu_eager_reference(args.workload, args.batch, min(args.steps, 10), 3)
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cb = 32
-            v_cpu, sec = time_cpu_reference(args.workload, cb, args.cpu_baseline_steps, 1, threads)
-            line["cpu_baseline"] = {"value": v_cpu, "unit": "samples/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_baseline_steps} engine steps of batch {cb} (same workload "
-                                              f"shape, fp32), {sec:.2f} s/step"}
+            v_cpu, sec, kind = time_cpu_reference(args.workload, args.batch, args.cpu_baseline_steps, 1, threads)
+            line["cpu_baseline"] = {"value": v_cpu, "unit": "samples/s", "cores": threads, "kind": kind,
+                                    "sample": f"{args.cpu_baseline_steps} engine steps of batch {args.batch} (same "
+                                              f"workload and batch, fp32, all host threads), {sec:.2f} s/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # no collective and no communicator teardown at exit: a rank that is done leaves immediately (rank 0 may still be

@@ -276,8 +276,11 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
                      : "memory");
       }
-      // the A tile is rewritten by the next branch / item and TMEM is read by the epilogue only after the MMAs retire
-      ok = mbar_wait(smem_u32(mbar), phase) && ok;
+      // the A tile is rewritten by the next branch / item and TMEM is read by the epilogue only after the MMAs retire.
+      // Only the issuing warp polls the mbarrier; the other 15 sleep at a block barrier (512 threads spinning on
+      // try_wait compete with the tensor core for shared-memory bandwidth and issue slots)
+      if (warp == 0) ok = mbar_wait(smem_u32(mbar), phase) && ok;
+      ok = __syncthreads_and(ok);
       phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }

@@ -311,10 +311,15 @@ class _DSTDGCNBase(nn.Module):
         self.conv_st_out = self._layer_cls(num_feature, input_channels // 2, [1, 1], 1, all_time_frame,
                                            joints_to_consider, True, True, False, layout)
         self.prelu = nn.PReLU()
-        self.dropout_mask = None      # test hook: explicit (already 1/(1-p)-scaled) [N,C,T,V] mask
+        self.dropout_mask = None      # test hook: explicit (already 1/(1-p)-scaled) [N,C,T,V] mask, or a list of masks
+        self._mask_calls = 0          # used in turn by consecutive forward calls (the two passes of a training step)
 
     def _mask(self, n, c, t, v, device):
         if self.dropout_mask is not None:
+            if isinstance(self.dropout_mask, (list, tuple)):
+                mk = self.dropout_mask[self._mask_calls % len(self.dropout_mask)]
+                self._mask_calls += 1
+                return mk
             return self.dropout_mask
         if self.training and self.do_in.p > 0:
             # torch's Philox stream draws the mask; applying it is fused into the BN/PReLU kernel

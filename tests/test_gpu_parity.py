@@ -393,6 +393,133 @@ def test_training_steps_vs_reference_golden(variant):
             assert int(sd[k]) == int(b), k
 
 
+def test_full_size_training_steps_with_dropout_vs_oracle():
+    """Five Adam steps of the engine loop at the shape and batch the bench times (C=64, L=5, batch 256, inverse pass,
+    dropout 0.1) against the fp64 oracle driven with the SAME dropout masks (one per forward pass, as the reference
+    draws them): loss trajectory within 1e-3 relative, or within 4x of what the fp32 oracle itself loses against fp64
+    (training tier)."""
+    from dstd_gcn_b200.engine import TrainStep
+    from oracle import dstd_oracle as orc
+    import bench
+    n, v, t_in, t_out, c, drop, steps = 256, 22, 10, 25, 64, 0.1, 5
+    t = t_in + t_out
+    torch.manual_seed(777)
+    m = _perturbed(_mod("std").DSTDGCN(6, t_in, t_out, drop, v, c, 5, "h36m"))
+    g = torch.Generator().manual_seed(99)
+    masks = [[(torch.rand(n, c, t, v, generator=g) >= drop).float() / (1.0 - drop) for _ in range(2)] for _ in range(steps)]
+    batches = [bench.synthetic_batch(n, t, v, t_in, seed=500 + s) for s in range(steps)]
+
+    def oracle_trajectory(dtype):
+        p = orc.state_from_module(m, dtype)
+        opt = torch.optim.Adam([x for x in p.values() if x.requires_grad], lr=3e-3)
+        out = []
+        for s in range(steps):
+            a, b, tg = (x.to(dtype) for x in batches[s])
+            loss = orc.train_loss(p, a, b, tg, dropout_masks=tuple(mk.to(dtype) for mk in masks[s]))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            out.append(float(loss.detach()))
+        return out
+
+    ref = oracle_trajectory(torch.float64)
+    ref32 = oracle_trajectory(torch.float32)          # the reference's own arithmetic: the yardstick for the divergence
+    md = m.to(DEV).train()
+    step = TrainStep(md, lr=3e-3, inverse=True)
+    got = []
+    for s in range(steps):
+        md.dropout_mask = [mk.to(DEV) for mk in masks[s]]
+        md._mask_calls = 0
+        got.append(float(step(*(x.to(DEV) for x in batches[s]))))
+    ref_t, got_t, r32_t = (torch.tensor(x, dtype=torch.float64) for x in (ref, got, ref32))
+    dev, dev32 = (got_t - ref_t).abs() / ref_t.abs(), (r32_t - ref_t).abs() / ref_t.abs()
+    # the first step has no accumulated divergence: 1e-4.  Later steps: Adam turns rounding-level gradient differences
+    # of small-gradient parameters into +-lr moves, so trajectories separate at a rate set by the arithmetic, not by
+    # the kernels; the fp32 oracle (torch CPU fp32) shows how fast: stay within 1e-3 or 4x of it
+    assert float(dev[0]) < 1e-4, (got, ref)
+    assert bool((dev <= torch.clamp(4 * dev32, min=1e-3)).all()), (got, ref, ref32)
+
+
+def test_device_error_word_is_reported_and_sticky():
+    """A kernel-side failure (the timeout of a tensor-core pipeline writes this word) must surface on the NEXT entry
+    point as an error, stay until cleared, and not poison later calls once cleared (include/dstd_b200.h)."""
+    lib = _lib.load_library()
+    be = cuda_backend()
+    g = torch.Generator().manual_seed(3)
+    x = to_dev(rnd((2, 8, 12, 22), g))
+    brs = dev_branches(make_branches(g, 2, 8, 8, 12, 22))
+    alpha = to_dev(rnd((1,), g))
+    be.gc_forward(x, alpha, brs, None, False)
+    torch.cuda.synchronize()
+    assert lib.dstd_device_error(0) == 0
+    assert lib.dstd_debug_raise_device_error(7, None) == 0
+    torch.cuda.synchronize()
+    assert lib.dstd_device_error(0) == 7
+    with pytest.raises(RuntimeError, match="device-side failure"):
+        be.gc_forward(x, alpha, brs, None, False)
+    with pytest.raises(RuntimeError, match="device-side failure"):        # sticky
+        be.gc_forward(x, alpha, brs, None, False)
+    assert lib.dstd_device_error(1) == 7 and lib.dstd_device_error(0) == 0
+    out, _, _, _ = be.gc_forward(x, alpha, brs, None, False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+
+
+def test_evaluate_and_checkpoint_on_the_cuda_path(tmp_path):
+    """`engine.evaluate` (PredictionEngine.test, engine/prediction.py:319-430) and the reference-format checkpoint
+    round trip with the model running on the sm_100a kernels."""
+    import numpy as np
+    from dstd_gcn_b200 import engine
+    from oracle import dstd_oracle as orc
+    torch.manual_seed(11)
+    m = _perturbed(_mod("std").DSTDGCN(6, 10, 25, 0.0, 22, 16, 2, "h36m")).to(DEV).train()
+    step = engine.TrainStep(m, lr=3e-3, inverse=True)
+    g = torch.Generator().manual_seed(5)
+    joints_full, t_all, input_n = 32, 35, 10
+    used_j = np.array([j for j in range(joints_full) if j not in (0, 1, 6, 11, 16, 20, 23, 24, 28, 31)])
+    dim_used = np.sort(np.concatenate([used_j * 3 + c for c in range(3)]))
+    ign, eq = np.array([16, 20, 23, 24, 28, 31]), np.array([13, 19, 22, 13, 27, 30])
+    eval_frame = [1, 3, 7, 9, 13, 24]
+    seqs = [torch.randn(n, t_all, joints_full * 3, generator=g) for n in (5, 3)]
+    for sq in seqs:                                   # two training steps move the BN running statistics off (0, 1)
+        x = sq[:, :, dim_used].to(DEV)
+        step(x.contiguous(), torch.flip(x, dims=[1]).contiguous(), x.contiguous())
+    batches = [(sq[:, :, dim_used].clone().to(DEV), sq.to(DEV)) for sq in seqs]
+    avg, per_frame = engine.evaluate(m, batches, input_n, eval_frame, dim_used, ign, eq)
+    assert m.training                                 # evaluate restores the mode
+    # restatement of the reference metric around the fp64 oracle forward in eval mode
+    p64 = {k: t.cpu() for k, t in orc.state_from_module(m, torch.float64).items()}
+    tot, cnt = np.zeros(len(eval_frame)), 0
+    for sq in seqs:
+        n = sq.shape[0]
+        out = orc.dstdgcn(sq[:, :, dim_used].double().view(n, t_all, 22, 3), p64, False, False).reshape(n, t_all, 66)
+        pred = sq.double().clone()
+        pred[:, :, dim_used] = out.detach()
+        i_ign = np.concatenate((ign * 3, ign * 3 + 1, ign * 3 + 2))
+        i_eq = np.concatenate((eq * 3, eq * 3 + 1, eq * 3 + 2))
+        pred[:, :, i_ign] = pred[:, :, i_eq]
+        p3 = pred.view(n, t_all, -1, 3)[:, input_n:]
+        t3 = sq.double().view(n, t_all, -1, 3)[:, input_n:]
+        for k, j in enumerate(eval_frame):
+            tot[k] += float(torch.linalg.vector_norm(t3[:, j] - p3[:, j], dim=-1).mean()) * n
+        cnt += n
+    ref_frames = tot / cnt
+    assert np.allclose(per_frame, ref_frames, rtol=2e-4, atol=1e-5), (per_frame, ref_frames)
+    assert abs(avg - ref_frames.mean()) < 2e-4 * max(1.0, abs(ref_frames.mean()))
+    # checkpoint round trip on the device: a second model continues bit-identically
+    path = str(tmp_path / "last.pth")
+    engine.save_checkpoint(path, step, err=avg, epoch=1)
+    m2 = _mod("std").DSTDGCN(6, 10, 25, 0.0, 22, 16, 2, "h36m").to(DEV).train()
+    step2 = engine.TrainStep(m2, lr=1.0, inverse=True)
+    epoch, err = engine.load_checkpoint(path, m2, step2)
+    assert epoch == 1 and abs(err - avg) < 1e-12 and step2.lr == 3e-3
+    x = seqs[0][:, :, dim_used].to(DEV).contiguous()
+    l1 = step(x, torch.flip(x, dims=[1]).contiguous(), x)
+    l2 = step2(x, torch.flip(x, dims=[1]).contiguous(), x)
+    assert float(l1) == float(l2)
+    assert torch.equal(step.flat.param, step2.flat.param)
+
+
 # ================================================================================================= full-size checks
 def _perturbed(m):
     with torch.no_grad():
@@ -412,8 +539,19 @@ def _perturbed(m):
 def test_full_size_model_vs_oracle(variant, layout, v, tin, tout):
     """BASELINE.json shapes (C=64, L=5): fp32 kernels vs the fp64 oracle.  At this depth the network amplifies fp32
     rounding by ~1e4 (the reference's own fp32-vs-fp64 error is 2e-3 abs / 4e-5 rel on y and 3e-3 rel on dx, SURVEY.md
-    section 4), so the yardstick is the fp32 oracle (= the reference's arithmetic) against the same fp64 truth: the
-    forward must be as good as that, every gradient within 30x of it or 3 % of the tensor's scale."""
+    section 4), so the yardstick is the fp32 oracle (= the reference's arithmetic) against the same fp64 truth.
+    Measured ratios ours / fp32-oracle per shape: profiles/r02_parity_ratios.md (y 2.9-3.2, dx 1.0-2.6, all parameter
+    gradients together 1.05-2.4); the gates sit just above the worst measured value."""
+    _full_size_check(variant, layout, v, tin, tout)
+
+
+def test_full_size_model_vs_oracle_all_tcgen05_path(monkeypatch):
+    """Same check through the opt-in all-tcgen05 unit kernels (unit_tc.cu, bf16x3 operands)."""
+    monkeypatch.setenv("DSTD_UNIT_TC", "1")
+    _full_size_check("std", "h36m", 22, 10, 25)
+
+
+def _full_size_check(variant, layout, v, tin, tout):
     from oracle import dstd_oracle as orc
     fast = variant == "fast"
     torch.manual_seed(777)
@@ -433,9 +571,9 @@ def test_full_size_model_vs_oracle(variant, layout, v, tin, tout):
     xd = x.float().to(DEV).requires_grad_(True)
     y = md(xd)
     y.pow(2).mean().backward()
-    assert rel_err(y, y64) < max(1e-4, 4 * rel_err(y32, y64))
-    assert rel_err(xd.grad, gx64) < max(1e-3, 10 * rel_err(gx32, gx64))
-    # all parameter gradients together: relative L2 error within 4x of what fp32 torch arithmetic loses (or 5e-3)
+    assert rel_err(y, y64) < 4 * rel_err(y32, y64)
+    assert rel_err(xd.grad, gx64) < 3.5 * rel_err(gx32, gx64)
+    # all parameter gradients together: relative L2 error within 3.5x of what fp32 torch arithmetic loses
     num = den = num32 = 0.0
     for k, p in md.named_parameters():
         if p.grad is None:
@@ -445,16 +583,19 @@ def test_full_size_model_vs_oracle(variant, layout, v, tin, tout):
         num32 += float(((g32[k].double() - g64[k]) ** 2).sum())
         den += float((g64[k] ** 2).sum())
     rel, rel32 = (num / den) ** 0.5, (num32 / den) ** 0.5
-    assert rel < max(5e-3, 4 * rel32), (rel, rel32)
-    # per tensor: bias-like gradients (plain sums of a zero-mean upstream gradient: PReLU slopes, alpha, conv_m biases,
-    # R_t) cancel by 1e3..1e4, so their relative error is that much larger than the error of the terms: 10 % of scale
+    assert rel < 3.5 * rel32, (rel, rel32)
+    # per tensor: within 10x of the fp32 oracle's own error (one realisation of fp32 rounding: the ratio of two such
+    # errors scatters by an order of magnitude), or 8 % of the tensor's scale (bias-like gradients -- PReLU slopes,
+    # alpha, conv_m biases, R_t -- are sums of a zero-mean upstream gradient that cancel by 1e3..1e4, so their relative
+    # error is that much above the error of the terms; measured worst: 5.8 % on a conv_m bias of scale 0.04 at the 3DPW
+    # shape, 2.2 % elsewhere), or 2e-6 of the largest gradient entry
     gmax = max(float(t.abs().max()) for t in g64.values())
     bad = []
     for k, p in md.named_parameters():
         if p.grad is None:
             continue
         e, e32, scale = max_abs(p.grad, g64[k]), max_abs(g32[k], g64[k]), float(g64[k].abs().max())
-        if e > max(30 * e32, 1e-1 * scale, 1e-6 * gmax):
+        if e > max(10 * e32, 8e-2 * scale, 2e-6 * gmax):
             bad.append((k, e, e32, scale))
     assert not bad, bad[:5]
 
