@@ -33,8 +33,18 @@ WORKLOADS = {
     "h36m": ("h36m", 22, 10, 25, 0.1),
     "cmu": ("cmu", 25, 10, 25, 0.1),
     "3dpw": ("3dpw", 23, 10, 30, 0.0),
+    "stress": ("h36m", 22, 50, 75, 0.1),     # BASELINE.json configs[4]: 50 -> 75 frames, 256 hidden channels
 }
-C_FEAT, N_LAYERS = 64, 5
+N_LAYERS = 5
+FEATURES = {"stress": 256}
+DEFAULT_BATCH = {"stress": 32}
+
+
+def feat(workload):
+    return FEATURES.get(workload, 64)
+
+
+C_FEAT = 64
 
 
 def dominant_call_roofline(batch, v, t, peak, c=C_FEAT, reps=5):
@@ -68,7 +78,7 @@ def dominant_call_roofline(batch, v, t, peak, c=C_FEAT, reps=5):
             "calls_per_step": 2 * N_LAYERS}
 
 
-def algorithmic_bytes_per_pass(v, t, c=C_FEAT, layers=N_LAYERS):
+def algorithmic_bytes_per_pass(v, t, c=64, layers=N_LAYERS):
     """one HBM round trip per DSTDGCB layer, fp32, forward + backward of one model pass."""
     chans = [(6, c)] + [(c, c)] * layers + [(c, 3)]
     fwd = 4 * t * v * sum(ci + co for ci, co in chans)
@@ -199,7 +209,7 @@ def reference_engine(workload, device):
     ref_model, ref_engine = ref
     layout, v, t_in, t_out, drop = WORKLOADS[workload]
     torch.manual_seed(777)
-    m = ref_model.DSTDGCN(6, t_in, t_out, drop, v, C_FEAT, N_LAYERS, layout)
+    m = ref_model.DSTDGCN(6, t_in, t_out, drop, v, feat(workload), N_LAYERS, layout)
     for p in m.parameters():            # what `.to("cuda")` does to the A_s / R_s alias
         p.data = p.data.clone()
     m = perturb(m).to(device)
@@ -225,7 +235,7 @@ def oracle_step_fn(workload, batch, threads, drop):
     t = t_in + t_out
     torch.set_num_threads(threads)
     torch.manual_seed(777)
-    m = perturb(std.DSTDGCN(6, t_in, t_out, 0.0, v, C_FEAT, N_LAYERS, layout))
+    m = perturb(std.DSTDGCN(6, t_in, t_out, 0.0, v, feat(workload), N_LAYERS, layout))
     p = orc.state_from_module(m, torch.float32)
     params = [x for x in p.values() if x.requires_grad]
     opt = torch.optim.Adam(params, lr=3e-3)
@@ -340,7 +350,7 @@ def run_reference_arm(args):
 def workload_config(args, batch_override=None):
     layout, v, t_in, t_out, drop = WORKLOADS[args.workload]
     b = batch_override if batch_override is not None else args.batch
-    return {"workload": f"DSTD-GCN {args.workload} shape ({v} joints, {t_in}->{t_out} frames, xyz), C={C_FEAT}, "
+    return {"workload": f"DSTD-GCN {args.workload} shape ({v} joints, {t_in}->{t_out} frames, xyz), C={feat(args.workload)}, "
                         f"L={N_LAYERS}, training step with inverse pass, batch {b} per GPU",
             "variant": "dstdgcn", "batch_per_gpu": b, "global_batch": b * args.gpus, "inverse": True,
             "dropout": drop, "l2_policy": "per-step working set (activations + saved tensors) >> 126 MB L2; "
@@ -407,7 +417,8 @@ def run_infer(args, model, be, dev, rank, world, t, v, t_in):
         sps, sps_e2e = total / (ms * 1e-3), total / (ms_e2e * 1e-3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
-        chans = [(6, C_FEAT)] + [(C_FEAT, C_FEAT)] * N_LAYERS + [(C_FEAT, 3)]
+        cf = feat(args.workload)
+        chans = [(6, cf)] + [(cf, cf)] * N_LAYERS + [(cf, 3)]
         bytes_fwd = 4 * t * v * sum(ci + co for ci, co in chans)
         achieved = sps / world * bytes_fwd / 1e9
         cfg = workload_config(args)
@@ -435,7 +446,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default 256; 32 for stress)")
     ap.add_argument("--workload", default="h36m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
@@ -448,6 +459,8 @@ def main():
                     help="--impl reference: budget of CPU work for the timed sample (0 = run exactly --steps)")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH.get(args.workload, 256)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
@@ -474,7 +487,7 @@ def main():
     layout, v, t_in, t_out, drop = WORKLOADS[args.workload]
     t = t_in + t_out
     torch.manual_seed(777)                       # identical replicas on every rank
-    model = perturb(std.DSTDGCN(6, t_in, t_out, drop, v, C_FEAT, N_LAYERS, layout)).to(dev).train()
+    model = perturb(std.DSTDGCN(6, t_in, t_out, drop, v, feat(args.workload), N_LAYERS, layout)).to(dev).train()
     be = _lib.backend()
     if args.mode == "infer":
         run_infer(args, model, be, dev, rank, world, t, v, t_in)
@@ -545,7 +558,7 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        bytes_pass = algorithmic_bytes_per_pass(v, t)
+        bytes_pass = algorithmic_bytes_per_pass(v, t, feat(args.workload))
         traffic = None      # measured DRAM bytes per step (ncu dram__bytes_read+write over every launch of one step)
         tpath = os.path.join(ROOT, "profiles", f"r01_dram_traffic_{args.workload}_b{args.batch}.json")
         if os.path.exists(tpath):
@@ -570,7 +583,7 @@ def main():
                          "algorithmic_bytes_per_sample": 2 * bytes_pass},
         }
         try:
-            line["roofline"]["dominant_call"] = dominant_call_roofline(args.batch, v, t, peak)
+            line["roofline"]["dominant_call"] = dominant_call_roofline(args.batch, v, t, peak, c=feat(args.workload))
         except Exception as e:      # never lose the bench line over the extra measurement
             line["roofline"]["dominant_call"] = {"error": repr(e)}
         if not args.no_gpu_eager_baseline:

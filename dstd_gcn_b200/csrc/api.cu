@@ -134,12 +134,15 @@ static size_t gc_fwd_ws(int Cin, int Cout, int nb, int P = 40, int K = 40) {
                      (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4, aggmix_tc_ws_floats(Cin, Cout, P, K, nb) * 4,
                      unit_tc_ws_bytes(nb)});
 }
+// shapes beyond the specialised tiles (P or K > 40) run the shape-generic kernels of generic.cu
+static bool use_generic(int Cin, int P, int K) { return !(dynadj_supported(P, K) && aggregate_supported(Cin, P, K)); }
+static int dyn_splits(int N, int nb, int Cin, int P, int K) { return use_generic(Cin, P, K) ? N : dynadj_bwd_splits(N, nb); }
 // per-CTA partial slots of the persistent kernels (one or two per SM)
 static size_t part_slots() { return (size_t)2 * num_sms(); }
 static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   const size_t C1 = Cin + 1, G = (size_t)N * P * K;
-  const int S1 = wgrad_splits((long long)G), S2 = dynadj_bwd_splits(N, nb);
-  const size_t unf = (unit_tc_supported(Cin, Cout, P, K, nb) || aggmix_bwd_supported(Cin, Cout, P, K, nb)) ? 0 : 1;   // buffers only the unfused path needs
+  const int S1 = wgrad_splits((long long)G), S2 = dyn_splits(N, nb, Cin, P, K);
+  const size_t unf = (!use_generic(Cin, P, K) && (unit_tc_supported(Cin, Cout, P, K, nb) || aggmix_bwd_supported(Cin, Cout, P, K, nb))) ? 0 : 1;   // buffers only the unfused path needs
   const size_t ps = part_slots();
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
                      G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, ((size_t)S1 > ps ? (size_t)S1 : ps) * 4 * nb * C1 * 4,
@@ -154,8 +157,8 @@ static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const
     DSTD_REQUIRE(br[b].w_m1 && br[b].b_m1 && br[b].w_m2 && br[b].b_m2 && br[b].w_rm && br[b].b_rm && br[b].w_f &&
                      br[b].b_f && br[b].adj,
                  DSTD_ERR_BAD_ARG, "%s: branch %d has a null weight", fn, b);
-  DSTD_REQUIRE(dynadj_supported(P, K) && aggregate_supported(Cin, P, K), DSTD_ERR_UNSUPPORTED,
-               "%s: unit shape P=%d K=%d outside the compiled tile limits (P<=40, K<=40)", fn, P, K);
+  DSTD_REQUIRE((dynadj_supported(P, K) && aggregate_supported(Cin, P, K)) || generic_supported(P, K), DSTD_ERR_UNSUPPORTED,
+               "%s: unit shape P=%d K=%d outside the compiled tile limits (P<=128, K<=128)", fn, P, K);
   return DSTD_OK;
 }
 
@@ -212,6 +215,7 @@ extern "C" int dstd_debug_raise_device_error(int code, dstd_stream_t stream) {
 }
 
 extern "C" int dstd_gc_needs_xa(int Cin, int Cout, int P, int K, int nb) {
+  if (use_generic(Cin, P, K)) return 1;
   if (unit_tc_supported(Cin, Cout, P, K, nb)) return 0;
   return (aggmix_supported(Cin, Cout, P, K, nb) && aggmix_bwd_supported(Cin, Cout, P, K, nb)) ? 0 : 1;
 }
@@ -244,7 +248,7 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   void* wunit = ar.take<char>(unit_tc_ws_bytes(nb));
   const bool use_unit = !a->xa && unit_tc_supported(Cin, Cout, P, K, nb);    // every contraction on tcgen05 (unit_tc.cu)
   const bool use_tc = !a->xa && aggmix_tc_supported(Cin, Cout, P, K, nb);   // tcgen05 channel mix only (aggmix_tc.cu)
-  const bool fused = use_unit || aggmix_supported(Cin, Cout, P, K, nb);
+  const bool fused = !use_generic(Cin, P, K) && (use_unit || aggmix_supported(Cin, Cout, P, K, nb));
 
   PackParams pk;
   fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm, fused ? wcatT : nullptr);
@@ -265,7 +269,8 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
     dp.w_rm[b] = a->br[b < nb ? b : 0].w_rm;
     dp.b_rm[b] = a->br[b < nb ? b : 0].b_rm;
   }
-  if ((rc = launch_dynadj_fwd(dp, st))) return rc;
+  const bool generic = use_generic(Cin, P, K);
+  if ((rc = generic ? launch_dynadj_fwd_gen(dp, st) : launch_dynadj_fwd(dp, st))) return rc;
 
   // 3+4 fused: out = wcat ([x;1] (alpha pd + A)) (+ skip); the aggregated tile stays in shared memory
   if (fused) {
@@ -292,7 +297,7 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   AggParams ag;
   fill_agg(ag, N, Cin, P, K, nb, a->flags, a->x, a->pd, a->alpha, a->br);
   ag.xa = a->xa;
-  if ((rc = launch_aggregate_fwd(ag, st))) return rc;
+  if ((rc = generic ? launch_aggregate_fwd_gen(ag, st) : launch_aggregate_fwd(ag, st))) return rc;
 
   // 4. out = [Wf_0 bf_0 | Wf_1 bf_1] xa (+ skip)
   BgemmParams g2;
@@ -318,12 +323,13 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
                a->ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const long long G = (long long)N * P * K;
-  const int S1 = wgrad_splits(G), S2 = dynadj_bwd_splits(N, nb);
+  const int S1 = wgrad_splits(G), S2 = dyn_splits(N, nb, Cin, P, K);
+  const bool generic = use_generic(Cin, P, K);
   Arena ar(a->ws, a->ws_bytes);
   float* wcat = ar.take<float>((size_t)Cout * nb * C1);
   float* wm = ar.take<float>((size_t)4 * nb * C1);
   const bool use_unit = unit_tc_supported(Cin, Cout, P, K, nb);
-  const bool fused = use_unit || aggmix_bwd_supported(Cin, Cout, P, K, nb);
+  const bool fused = !generic && (use_unit || aggmix_bwd_supported(Cin, Cout, P, K, nb));
   const size_t ps = part_slots();
   float* gxa = ar.take<float>(fused ? 0 : (size_t)G * nb * C1);
   float* gxm = ar.take<float>((size_t)G * nb * K);
@@ -391,7 +397,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   ag.gxa = gxa;
   ag.gx = mk(a->gx);
   ag.gxm = gxm;
-  if ((rc = launch_aggregate_bwd(ag, st))) return rc;
+  if ((rc = generic ? launch_aggregate_bwd_gen(ag, st) : launch_aggregate_bwd(ag, st))) return rc;
   }
 
   // 4. dynamic adjacency backward: gm, partial gWrm/gbrm, gA_eff, galpha
@@ -403,7 +409,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
     db.b_rm[b] = a->br[b < nb ? b : 0].b_rm;
   }
   db.S = S2; db.part_wrm = p_wrm; db.part_adj = p_adj; db.part_alpha = p_alpha;
-  if ((rc = launch_dynadj_bwd(db, st))) return rc;
+  if ((rc = generic ? launch_dynadj_bwd_gen(db, st) : launch_dynadj_bwd(db, st))) return rc;
 
   // 5+6. gx += wm^T gm ; g(wm)[j, c] = sum gm[j] [x;1][c]   (one pass over x)
   int S1b = 0;

@@ -122,6 +122,13 @@ int launch_aggregate_fwd(const AggParams& q, cudaStream_t st);
 int launch_aggregate_bwd(const AggParams& q, cudaStream_t st);
 bool aggregate_supported(int Cin, int P, int K);
 
+// ------------------------------------------------------------------ generic.cu (P or K > 40: the stress configuration)
+bool generic_supported(int P, int K);
+int launch_dynadj_fwd_gen(const DynAdjFwdParams& q, cudaStream_t st);
+int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, cudaStream_t st);     // q.S == q.N partial slots
+int launch_aggregate_fwd_gen(const AggParams& q, cudaStream_t st);
+int launch_aggregate_bwd_gen(const AggParams& q, cudaStream_t st);
+
 // ------------------------------------------------------------------ aggmix.cu
 struct AggMixParams {
   int N, Cin, Cout, P, K, nb, adj_t;

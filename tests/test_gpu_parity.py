@@ -133,13 +133,63 @@ def test_gc_unit_abi_wide_channels_unfused_path():
     assert _lib.load_library().dstd_gc_needs_xa(64, 64, 35, 22, 2) == 0
 
 
+STRESS_CASES = [
+    # the stress configuration of BASELINE.json (T = 125, C = 256) runs the shape-generic kernels (csrc/generic.cu)
+    (1, 6, 24, 125, 22, 2, "pk", False, False),     # input block, spatial: P = 125 frames
+    (2, 24, 24, 22, 125, 1, "kp", False, True),     # temporal unit: K = 125 frames, layer skip, transposed view
+    (1, 72, 80, 125, 22, 2, "pk", False, False),    # wide channels, spatial
+    (1, 16, 3, 22, 125, 1, "pk", True, False),      # output-like block, adjacency used transposed
+]
+
+
+@pytest.mark.parametrize("case", STRESS_CASES, ids=[str(i) for i in range(len(STRESS_CASES))])
+def test_gc_unit_abi_stress_shapes(case):
+    test_gc_unit_abi(case)
+    n, cin, cout, p, k, nb = case[:6]
+    assert _lib.load_library().dstd_gc_needs_xa(cin, cout, p, k, nb) == 1
+
+
+def test_stress_config_model_vs_oracle():
+    """BASELINE.json configs[4]: H3.6M joints, 50 -> 75 frames, 256 hidden channels (DSTDGCN(6, 50, 75, ., 22, 256, 5)):
+    forward and every gradient against the fp64 oracle with the fp32 oracle as yardstick (same gates as the full-size
+    test of the dataset shapes)."""
+    from oracle import dstd_oracle as orc
+    torch.manual_seed(777)
+    m = _perturbed(_mod("std").DSTDGCN(6, 50, 75, 0.0, 22, 256, 5, "h36m"))
+    x = torch.randn(2, 125, 22, 3, generator=torch.Generator().manual_seed(1234), dtype=torch.float64)
+
+    def run_oracle(dtype):
+        p = orc.state_from_module(m, dtype)
+        xx = x.to(dtype).clone().requires_grad_(True)
+        y = orc.dstdgcn(xx, p, True, False)
+        y.pow(2).mean().backward()
+        return y.detach(), xx.grad, {k: t.grad for k, t in p.items() if t.requires_grad and t.grad is not None}
+
+    y64, gx64, g64 = run_oracle(torch.float64)
+    y32, gx32, g32 = run_oracle(torch.float32)
+    md = m.to(DEV).train()
+    xd = x.float().to(DEV).requires_grad_(True)
+    y = md(xd)
+    y.pow(2).mean().backward()
+    assert rel_err(y, y64) < max(1e-4, 4 * rel_err(y32, y64))
+    assert rel_err(xd.grad, gx64) < max(1e-3, 4 * rel_err(gx32, gx64))
+    num = den = num32 = 0.0
+    for k, p in md.named_parameters():
+        if p.grad is None:
+            continue
+        num += float(((p.grad.double().cpu() - g64[k]) ** 2).sum())
+        num32 += float(((g32[k].double() - g64[k]) ** 2).sum())
+        den += float((g64[k] ** 2).sum())
+    assert (num / den) ** 0.5 < max(1e-3, 4 * (num32 / den) ** 0.5), ((num / den) ** 0.5, (num32 / den) ** 0.5)
+
+
 def test_gc_unit_errors():
     be = cuda_backend()
     g = torch.Generator().manual_seed(5)
-    x = to_dev(rnd((1, 4, 50, 8), g))
-    brs = dev_branches(make_branches(g, 1, 4, 4, 50, 8))
+    x = to_dev(rnd((1, 4, 130, 8), g))
+    brs = dev_branches(make_branches(g, 1, 4, 4, 130, 8))
     with pytest.raises(RuntimeError, match="tile limits"):
-        be.gc_forward(x, None, brs, None, False)          # P > 40: outside the compiled limits -> loud error
+        be.gc_forward(x, None, brs, None, False)          # P > 128: outside the compiled limits -> loud error
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         be.gc_forward(x.cpu(), None, brs, None, False)     # no CPU fallback
 
