@@ -435,8 +435,20 @@ def run_infer(args, model, be, dev, rank, world, t, v, t_in):
                          "traffic": None, "scope": f"forward only: {bytes_fwd} algorithmic B per sample (SURVEY.md 8d)"},
         }), flush=True)
     if world > 1:
+        shutdown(dist, torch)
+
+
+def shutdown(dist, torch):
+    """Orderly multi-rank exit: a barrier (rank 0 may arrive late, it times the CPU / eager baselines after the bench;
+    the NCCL watchdog allows 10 minutes), then the communicator is destroyed.  Round 1 left through ``os._exit``."""
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    try:
+        dist.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
+        dist.destroy_process_group()
+    except Exception as e:          # never lose the printed line over teardown
+        print(f"bench: teardown failed ({e!r}); leaving", file=sys.stderr, flush=True)
         os._exit(0)
 
 
@@ -452,6 +464,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train: the headline metric; infer: eval-mode forward sweep (BASELINE.json config 4)")
     ap.add_argument("--variant", default="dstdgcn", choices=["dstdgcn", "dstdgcn_fast"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch samples per GPU; strong: --batch is the GLOBAL batch, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
@@ -461,6 +475,12 @@ def main():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH.get(args.workload, 256)
+    args.global_batch_fixed = None
+    if args.scaling == "strong":
+        world_env = int(os.environ.get("WORLD_SIZE", "1"))
+        assert args.batch % world_env == 0, "--scaling strong: the global batch must divide by the number of ranks"
+        args.global_batch_fixed = args.batch
+        args.batch = args.batch // world_env
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
@@ -568,7 +588,7 @@ def main():
         h2d = sum(x.numel() * 4 for x in host[0])
         line = {
             "metric": "train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "model_passes_per_s": 2.0 * sps,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -599,11 +619,7 @@ def main():
                                               f"workload and batch, fp32, all host threads), {sec:.2f} s/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        # no collective and no communicator teardown at exit: a rank that is done leaves immediately (rank 0 may still be
-        # timing the CPU baseline), and NCCL teardown after graph replays has been seen to block on this stack
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
+        shutdown(dist, torch)
 
 
 if __name__ == "__main__":
