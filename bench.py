@@ -452,6 +452,48 @@ def shutdown(dist, torch):
         os._exit(0)
 
 
+def secondary_lines(args, std, dev, resident, layout, v, t_in, t_out, drop):
+    """Secondary measurements of the same training step (never the headline): the opt-in all-tcgen05 unit kernels at
+    full fp32 parity, and their stated-tolerance modes (DSTD_PRECISION) that show how much of the step is the price of
+    1e-4 parity.  Same model, batch, CUDA-graph capture and CUDA-event timing as the main line."""
+    import torch
+    from dstd_gcn_b200.engine import TrainStep
+    out = {}
+    modes = [("all_tcgen05_fp32_parity", {"DSTD_UNIT_TC": "1"}, "six bf16 split products per k-step (x = h + m + l): fp32 parity, max-abs 1e-4"),
+             ("bf16x2", {"DSTD_PRECISION": "bf16x2"}, "three split products (hh + hm + mh): relative error <= 3e-4 per unit"),
+             ("bf16", {"DSTD_PRECISION": "bf16"}, "plain bf16 operands, fp32 accumulate: relative error <= 3e-2 per unit")]
+    for name, env, what in modes:
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            torch.manual_seed(777)
+            m = perturb(std.DSTDGCN(6, t_in, t_out, drop, v, feat(args.workload), N_LAYERS, layout)).to(dev).train()
+            st = TrainStep(m, lr=3e-3, inverse=True)
+            st.capture(*resident[0])
+            for i in range(3):
+                st(*resident[i % len(resident)])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k = max(3, min(args.steps, 10))
+            e0.record()
+            for i in range(k):
+                st(*resident[i % len(resident)])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / k
+            out[name] = {"value": args.batch / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": k,
+                         "precision": what}
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+        finally:
+            for k2, v2 in old.items():
+                if v2 is None:
+                    os.environ.pop(k2, None)
+                else:
+                    os.environ[k2] = v2
+    return out
+
+
 # =============================================================================================== GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -467,6 +509,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch samples per GPU; strong: --batch is the GLOBAL batch, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the stated-tolerance / all-tcgen05 secondary lines")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=90.0,
@@ -560,6 +603,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), (launches_per_step * k if launches_per_step is not None else be.launches - l0)
 
+    secondary = None
     run_resident(args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -568,6 +612,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     run_e2e(2)
     ms_e2e, _ = timed(run_e2e, args.steps)
+    if world == 1 and not args.no_secondary and not args.no_graph:
+        secondary = secondary_lines(args, std, dev, resident, layout, v, t_in, t_out, drop)
 
     if rank == 0:
         total = args.batch * world * args.steps
@@ -606,6 +652,8 @@ def main():
             line["roofline"]["dominant_call"] = dominant_call_roofline(args.batch, v, t, peak, c=feat(args.workload))
         except Exception as e:      # never lose the bench line over the extra measurement
             line["roofline"]["dominant_call"] = {"error": repr(e)}
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary
         if not args.no_gpu_eager_baseline:
             try:
                 line["gpu_eager_baseline"] = time_gpu_eager_reference(args.workload, args.batch, min(args.steps, 10), 3)

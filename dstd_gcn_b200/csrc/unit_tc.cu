@@ -50,6 +50,7 @@ struct UnitGeom {
   int plane_b, sbo_b;                  // [64][Q] plane
   int xr, xq, xplane_b, xsbo_b;        // xmu images [xr][xq]
   int tmem_cols;
+  int terms;                           // split products per k-step: 6 (fp32 parity), 3 or 1 (DSTD_PRECISION, stated tolerance)
   int o_x0, o_g1, o_s, o_w, o_xmu, o_aeff, o_bias, o_etab, o_gst, o_pst, o_pout, o_pskip, o_bar;   // shared-memory byte offsets
   int smem;
 };
@@ -235,12 +236,13 @@ struct Fam {
   uint32_t a_ks, b_ks, a_pl, b_pl;         // 16-byte units: per k-step, per split plane
   uint32_t d_inc, a_inc, b_inc;            // per chain (TMEM columns, 16-byte units)
   uint32_t idesc;
-  int nrep, ksteps;
+  int nrep, ksteps, terms;
   bool acc;
 };
-__device__ __forceinline__ Fam make_fam(uint32_t tmem_d, const OpView& a, const OpView& b, int ksteps, uint32_t idesc, bool acc,
-                                        int nrep = 1, uint32_t d_inc = 0, uint32_t a_inc_b = 0, uint32_t b_inc_b = 0) {
+__device__ __forceinline__ Fam make_fam(int terms, uint32_t tmem_d, const OpView& a, const OpView& b, int ksteps, uint32_t idesc,
+                                        bool acc, int nrep = 1, uint32_t d_inc = 0, uint32_t a_inc_b = 0, uint32_t b_inc_b = 0) {
   Fam f;
+  f.terms = terms;
   f.d = tmem_d;
   f.a_hi = (a.sbo_b >> 4) | (1u << 14);
   f.b_hi = (b.sbo_b >> 4) | (1u << 14);
@@ -272,8 +274,8 @@ __device__ __forceinline__ void issue_fams(const Fam& x, const Fam& y) {
 #pragma unroll
     for (int t = 0; t < 6; ++t) {            // hh hm mh mm hl lh
       const uint32_t ta = (t == 2 || t == 3) ? 1u : (t == 5 ? 2u : 0u), tb = (t == 1 || t == 3) ? 1u : (t == 4 ? 2u : 0u);
-      if (ks < x.ksteps) fam_product(x, xa, xb, ta, tb, (x.acc || ks > 0 || t > 0) ? 1u : 0u, leader);
-      if (TWO && ks < y.ksteps) fam_product(y, ya, yb, ta, tb, (y.acc || ks > 0 || t > 0) ? 1u : 0u, leader);
+      if (ks < x.ksteps && t < x.terms) fam_product(x, xa, xb, ta, tb, (x.acc || ks > 0 || t > 0) ? 1u : 0u, leader);
+      if (TWO && ks < y.ksteps && t < y.terms) fam_product(y, ya, yb, ta, tb, (y.acc || ks > 0 || t > 0) ? 1u : 0u, leader);
     }
   }
 }
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_fwd_tc_kernel(UnitFwdParams q, 
     UT_PH(9);
     if (warp == 0) {      // F1: xf = [Wf_0; Wf_1] x (one M = 128 chain for both branches)
       fence_after();
-      issue1(make_fam(d1, view_k(sw, 8 * IMG16_LBO_B, nb * UT_WP_B, 0), view_mn(sx0, g.sbo_b, g.plane_b, 0), g.CinK / 16, id_f1,
+      issue1(make_fam(g.terms, d1, view_k(sw, 8 * IMG16_LBO_B, nb * UT_WP_B, 0), view_mn(sx0, g.sbo_b, g.plane_b, 0), g.CinK / 16, id_f1,
                       false, f1_rep, f1_n, 0, (uint32_t)(f1_n >> 3) * IMG16_LBO_B));
       commit_elect(mbar);
       __syncwarp();
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_fwd_tc_kernel(UnitFwdParams q, 
       UT_PH(4);
       if (warp == 0) {    // F2: out[:, frame l] += xf_b[:, frame l] xmu_b[l]
         fence_after();
-        issue1(make_fam(dout, view_k(ss, g.sbo_b, g.plane_b, 0), view_mn(sxm + (uint32_t)(b * g.F) * 3 * g.xplane_b, g.xsbo_b, g.xplane_b, 0),
+        issue1(make_fam(g.terms, dout, view_k(ss, g.sbo_b, g.plane_b, 0), view_mn(sxm + (uint32_t)(b * g.F) * 3 * g.xplane_b, g.xsbo_b, g.xplane_b, 0),
                         g.KW / 16, id_f2, b > 0, g.F, g.KQ, (uint32_t)(g.KQ >> 3) * IMG16_LBO_B, 3u * g.xplane_b));
         commit_elect(mbar);
         __syncwarp();
@@ -649,10 +651,10 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_bwd_tc_kernel(UnitBwdParams q, 
       const uint32_t swb = sw + b * UT_WP_B;
       if (warp == 0) {    // B1: xf = [Wf_0; Wf_1] x (once per item) ; B2: h_b[:, frame l] = gout[:, frame l] xmu_b[l]^T
         fence_after();
-        Fam f1 = make_fam(d1, view_k(sw, 8 * IMG16_LBO_B, nb * UT_WP_B, 0), view_mn(sx0, g.sbo_b, g.plane_b, 0), g.CinK / 16, id_b1,
+        Fam f1 = make_fam(g.terms, d1, view_k(sw, 8 * IMG16_LBO_B, nb * UT_WP_B, 0), view_mn(sx0, g.sbo_b, g.plane_b, 0), g.CinK / 16, id_b1,
                           false, b1_rep, b1_n, 0, (uint32_t)(b1_n >> 3) * IMG16_LBO_B);
         if (b > 0) f1.ksteps = 0;
-        issue2(f1, make_fam(d2, view_k(sg1, g.sbo_b, g.plane_b, 0), view_k(sxm + (uint32_t)(b * g.F) * 3 * g.xplane_b, g.xsbo_b, g.xplane_b, 0),
+        issue2(f1, make_fam(g.terms, d2, view_k(sg1, g.sbo_b, g.plane_b, 0), view_k(sxm + (uint32_t)(b * g.F) * 3 * g.xplane_b, g.xsbo_b, g.xplane_b, 0),
                             g.KW / 16, id_b2, false, g.F, g.KQ, (uint32_t)(g.KQ >> 3) * IMG16_LBO_B, 3u * g.xplane_b));
         commit_elect(mbar);
         __syncwarp();
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_bwd_tc_kernel(UnitBwdParams q, 
       UT_PH(3);
       if (warp == 0) {    // B3: G[(l,v)][(l',w)] = sum_o xf_b[o][l,v] gout[o][l',w]: ONE M = 128 chain over all frame pairs (the
         fence_after();    // per-frame M = 64, N = KQ products cost ~46 cycles each however small); gxmu_b[l] = block (l, l)
-        issue1(make_fam(d3, view_mn(ss, g.sbo_b, g.plane_b, 0), view_mn(sg1, g.sbo_b, g.plane_b, 0), g.CoutK / 16, id_b3, false,
+        issue1(make_fam(g.terms, d3, view_mn(ss, g.sbo_b, g.plane_b, 0), view_mn(sg1, g.sbo_b, g.plane_b, 0), g.CoutK / 16, id_b3, false,
                         b3_rep, b3_n, 0, (uint32_t)(b3_n >> 3) * IMG16_LBO_B));
         commit_elect(mbar);
         __syncwarp();
@@ -713,8 +715,8 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_bwd_tc_kernel(UnitBwdParams q, 
       UT_PH(6);
       if (warp == 0) {    // B4: gx += Wf_b^T h_b ; B5: gWf_b += h_b x^T
         fence_after();
-        issue2(make_fam(d4, view_mn(swb, 8 * IMG16_LBO_B, nb * UT_WP_B, 0), view_mn(ss, g.sbo_b, g.plane_b, 0), g.CoutK / 16, id_b4, b > 0),
-               make_fam(d5 + b * g.CinN, view_k(ss, g.sbo_b, g.plane_b, 0), view_k(sx0, g.sbo_b, g.plane_b, 0), g.Q / 16, id_b5, !first));
+        issue2(make_fam(g.terms, d4, view_mn(swb, 8 * IMG16_LBO_B, nb * UT_WP_B, 0), view_mn(ss, g.sbo_b, g.plane_b, 0), g.CoutK / 16, id_b4, b > 0),
+               make_fam(g.terms, d5 + b * g.CinN, view_k(ss, g.sbo_b, g.plane_b, 0), view_k(sx0, g.sbo_b, g.plane_b, 0), g.Q / 16, id_b5, !first));
         commit_elect(mbar);
         __syncwarp();
       }
@@ -818,12 +820,21 @@ __global__ void pack_w16_kernel(PackParams q, unsigned char* wimg) {
 }
 
 // ------------------------------------------------------------------------------------------ geometry / launch
+// DSTD_PRECISION (secondary, stated-tolerance modes; the default "fp32" is the parity path): "bf16x2" keeps the products
+// hh + hm + mh (relative error ~2^-15), "bf16" only hh (plain bf16 operands, fp32 accumulate, ~2^-8).  Both run on these
+// kernels (there is no other reduced-precision implementation), so they imply DSTD_UNIT_TC=1.
+static int unit_terms() {
+  const char* p = getenv("DSTD_PRECISION");
+  if (p && p[0] == 'b' && p[1] == 'f' && p[2] == '1' && p[3] == '6') return (p[4] == 'x' && p[5] == '2') ? 3 : 1;
+  return 6;
+}
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // bwd: X0, G1 and scratch images; fwd: X0 and scratch.  The largest F (frames per item) that fits 227 KB wins.
 static bool unit_geom(int Cin, int Cout, int P, int K, int nb, bool bwd, UnitGeom& g) {
   if (K < 1 || K > 40 || K * ((K + 1) / 2) > 2 * UT_NT || Cin < 1 || Cin > 64 || Cout < 1 || Cout > 64 || nb < 1 || nb > DSTD_MAX_BRANCH) return false;
   g.KQ = round_up(K, 8);
+  g.terms = unit_terms();
   g.KW = round_up(K, 16);
   g.CinK = round_up(Cin, 16);
   g.CoutK = round_up(Cout, 16);
@@ -878,7 +889,7 @@ static bool unit_geom(int Cin, int Cout, int P, int K, int nb, bool bwd, UnitGeo
 // tests flip it to cover both paths.
 static bool unit_tc_enabled() {
   const char* on = getenv("DSTD_UNIT_TC");
-  return on && on[0] == '1';
+  return (on && on[0] == '1') || unit_terms() != 6;
 }
 
 bool unit_tc_supported(int Cin, int Cout, int P, int K, int nb) {

@@ -126,6 +126,38 @@ def test_gc_unit_abi_cuda_core_forward(case, monkeypatch):
     test_gc_unit_abi(case)
 
 
+@pytest.mark.parametrize("case", [GC_CASES[0], GC_CASES[2], GC_CASES[3], GC_CASES[4], GC_CASES[5], GC_CASES[6], GC_CASES[7],
+                                  GC_CASES[8]], ids=["in", "enc_spatial", "temporal_skip", "out_3dpw", "out_t_cmu", "fast", "tiny",
+                                                     "enc_3dpw"])
+def test_gc_unit_abi_all_tcgen05_path(case, monkeypatch):
+    """The same fp32-parity checks through the opt-in all-tcgen05 unit kernels (unit_tc.cu: bf16x3 operands, six split
+    products per k-step, every contraction of forward and backward on the tensor cores)."""
+    monkeypatch.setenv("DSTD_UNIT_TC", "1")
+    test_gc_unit_abi(case)
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x2", 3e-4), ("bf16", 3e-2)])
+def test_gc_unit_reduced_precision_modes(mode, tol, monkeypatch):
+    """DSTD_PRECISION: stated-tolerance modes of the all-tcgen05 kernels (secondary bench line, never the default).
+    bf16x2 = products hh + hm + mh (relative L2 error <= 3e-4), bf16 = hh only (<= 3e-2)."""
+    monkeypatch.setenv("DSTD_PRECISION", mode)
+    n, cin, cout, p, k, nb = 2, 64, 64, 35, 22, 2
+    g = torch.Generator().manual_seed(17)
+    be = cuda_backend()
+    x, gout = unit_input(g, n, cin, p, k, "pk"), unit_input(g, n, cout, p, k, "pk")
+    alpha = rnd((1,), g, 0.3) + 0.5
+    brs = make_branches(g, nb, cin, cout, p, k)
+    out_r, m_r, pd_r, xa_r = EM.gc_forward(x, alpha, brs, None, False)
+    gx_r, ga_r, gr_r = EM.gc_backward(x, gout, alpha, brs, m_r, pd_r, xa_r, False)
+    xd, ad, bd = to_dev(x), to_dev(alpha), dev_branches(brs)
+    out, m, pd, xa = be.gc_forward(xd, ad, bd, None, False)
+    gx, ga, gr = be.gc_backward(xd, to_dev(gout), ad, bd, m, pd, xa, False)
+    torch.cuda.synchronize()
+    assert rel_err(out, out_r) < tol and rel_err(gx, gx_r) < tol
+    assert rel_err(gr[0]["w_f"], gr_r[0]["w_f"]) < tol and rel_err(gr[1]["b_f"], gr_r[1]["b_f"]) < tol
+    assert rel_err(out, out_r) > 1e-6      # the mode is really active (the parity path is ~1e-7)
+
+
 def test_gc_unit_abi_wide_channels_unfused_path():
     """Cin, Cout > 64: outside the fused kernels' tile limits -> aggregate + bgemm + wgrad path that keeps xa."""
     test_gc_unit_abi((2, 80, 72, 12, 22, 2, "pk", False, True))
