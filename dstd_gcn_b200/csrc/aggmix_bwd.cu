@@ -13,6 +13,7 @@
 // HBM traffic per sample: x, gout read once, gx written once, pd read / gxm written once (K/ C of a tile each).
 // The per-CTA weight-gradient partials are summed by reduce_segments (deterministic, fixed order).
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace dstd {
 
@@ -62,6 +63,15 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
   const int nchunk = (P + PCH - 1) / PCH;
   const long long nitems = (long long)q.N * nchunk;
+  // the raw dynamic adjacency of an item is one contiguous block per branch: when K*K*4 is a multiple of 16 it is
+  // staged by the TMA engine (cp.async.bulk, one instruction per branch) instead of one 4-byte cp.async per element
+  __shared__ uint64_t pd_bar;
+  const bool pd_bulk = (KK & 3) == 0 && (reinterpret_cast<uintptr_t>(q.pd) & 15) == 0;
+  uint32_t pd_phase = 0;
+  if (tid == 0) {
+    umma::mbar_init(&pd_bar, 1);
+    umma::mbar_init_fence();
+  }
 
   // ---- once per CTA: weights
   for (int i = tid; i < nb * CoutR8 * WS; i += AMB_NT) {
@@ -140,9 +150,17 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
         for (int i = 0; i < TN; ++i)
           if (lane + 32 * i < npos_pad) cp_async4(gos + c * LD + lane + 32 * i, gb + (long long)c * q.gout.sc + poff_g[i], pok[i]);
       }
-      for (int b = 0; b < nb; ++b) {
-        const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
-        for (int i = tid; i < pv * KK; i += AMB_NT) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+      if (pd_bulk) {
+        if (tid == 0) {
+          umma::mbar_expect_tx(&pd_bar, (uint32_t)(nb * pv * KK * 4));
+          for (int b = 0; b < nb; ++b)
+            umma::bulk_g2s(pdr + b * PCH * KK, q.pd + ((long long)(n * nb + b) * P + p0) * KK, (uint32_t)(pv * KK * 4), &pd_bar);
+        }
+      } else {
+        for (int b = 0; b < nb; ++b) {
+          const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
+          for (int i = tid; i < pv * KK; i += AMB_NT) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+        }
       }
       if (warp == 0) {
 #pragma unroll
@@ -150,6 +168,10 @@ __global__ void __launch_bounds__(AMB_NT, 1) aggmix_bwd_kernel(AggMixBwdParams q
           if (lane + 32 * i < npos_pad) xs[Cin * LD + lane + 32 * i] = pok[i] ? 1.0f : 0.f;
       }
       cp_async_wait_all();
+      if (pd_bulk) {
+        umma::mbar_wait(&pd_bar, pd_phase);
+        pd_phase ^= 1;
+      }
       __syncthreads();
       PH(0);
       // element-parallel (8 independent elements per thread); the row decode comes from a table built once per CTA, so

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace dstd {
 
@@ -101,10 +102,19 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
   const int nchunk = (P + PCH - 1) / PCH;
   const long long nitems = (long long)q.N * nchunk;
 
+  // TMA bulk copies (cp.async.bulk): the weight image once per CTA, the raw dynamic adjacency of every item (one
+  // contiguous block per branch) when K*K*4 is a multiple of 16; otherwise 4-byte cp.async per element
+  __shared__ uint64_t pd_bar;
+  const bool pd_bulk = (KK & 3) == 0 && (reinterpret_cast<uintptr_t>(q.pd) & 15) == 0;
+  uint32_t pd_phase = 0;
   // ---- once per CTA: resident weights, static adjacency, zeroed A tiles (pad rows of K must read as 0), TMEM, mbarrier
   {
-    const int n4 = nb * 2 * b_tile_f / 4;
-    for (int i = tid; i < n4; i += TC_NT) cp_async16(b_img + 4 * i, q.wtc + 4 * i);
+    if (tid == 0) {
+      umma::mbar_init(&pd_bar, 1);
+      umma::mbar_init_fence();
+      umma::mbar_expect_tx(&pd_bar, (uint32_t)(nb * 2 * b_tile_f * 4));
+      umma::bulk_g2s(b_img, q.wtc, (uint32_t)(nb * 2 * b_tile_f * 4), &pd_bar);
+    }
     for (int i = tid; i < 2 * a_tile_f; i += TC_NT) a_hi[i] = 0.f;
     for (int i = tid; i < nb * KK; i += TC_NT) {
       const int b = i / KK, e = i - b * KK;
@@ -123,7 +133,9 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < nb * PCH * K; i += TC_NT) rowtab[i] = ((i / K) << 8) | (i % K);
-    cp_async_wait_all();
+    __syncthreads();               // the barrier initialisation is visible to every waiter
+    umma::mbar_wait(&pd_bar, pd_phase);
+    pd_phase ^= 1;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -155,9 +167,17 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
         for (int i = 0; i < TNS; ++i)
           if (poff[i] >= 0) cp_async4(xs + c * XS_LD + lane + 32 * i, xb + (long long)c * q.x.sc + poff[i], true);
       }
-      for (int b = 0; b < nb; ++b) {
-        const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
-        for (int i = tid; i < pv * KK; i += TC_NT) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+      if (pd_bulk) {
+        if (tid == 0) {
+          umma::mbar_expect_tx(&pd_bar, (uint32_t)(nb * pv * KK * 4));
+          for (int b = 0; b < nb; ++b)
+            umma::bulk_g2s(pdr + b * PCH * KK, q.pd + ((long long)(n * nb + b) * P + p0) * KK, (uint32_t)(pv * KK * 4), &pd_bar);
+        }
+      } else {
+        for (int b = 0; b < nb; ++b) {
+          const float* pdl = q.pd + ((long long)(n * nb + b) * P + p0) * KK;
+          for (int i = tid; i < pv * KK; i += TC_NT) cp_async4(pdr + b * PCH * KK + i, pdl + i, true);
+        }
       }
       if (q.skip.p) {
         // lane order (k major, l minor) when the skip is contiguous along p, else the position order
@@ -179,6 +199,10 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
         }
       }
       cp_async_wait_all();
+      if (pd_bulk) {
+        umma::mbar_wait(&pd_bar, pd_phase);
+        pd_phase ^= 1;
+      }
       __syncthreads();
       // element-parallel; the row decode comes from a table built once per CTA (no runtime division in the loop)
       for (int i = tid; i < nb * PCH * K * KP; i += TC_NT) {

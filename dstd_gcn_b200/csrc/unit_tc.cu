@@ -389,9 +389,6 @@ __device__ __forceinline__ uint32_t unit_setup(const Q& q, const UnitGeom& g, un
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + g.o_bar);
   uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int K = q.K, KK = K * K;
-  const int nchunks = q.nb * 3 * UT_WP_B / 16;
-  for (int i = tid; i < nchunks; i += UT_NT)
-    cp_async16(reinterpret_cast<float*>(smem + g.o_w) + 4 * i, reinterpret_cast<const float*>(wimg) + 4 * i);
   for (int i = tid; i < q.nb * KK; i += UT_NT) {
     const int b = i / KK, e = i - b * KK;
     float a = __ldg(q.adj[b] + e);
@@ -423,16 +420,18 @@ __device__ __forceinline__ uint32_t unit_setup(const Q& q, const UnitGeom& g, un
     uint32_t* z = reinterpret_cast<uint32_t*>(smem + g.o_xmu);
     for (int i = tid; i < q.nb * g.F * 3 * g.xplane_b / 4; i += UT_NT) z[i] = 0u;
   }
-  if (tid == 0) {
+  if (tid == 0) {         // weight images: one TMA bulk copy (cp.async.bulk) counted on the MMA barrier's first phase
     mbar_init(mbar, 1);
     mbar_init_fence();
+    mbar_expect_tx(mbar, (uint32_t)(q.nb * 3 * UT_WP_B));
+    bulk_g2s(smem + g.o_w, wimg, (uint32_t)(q.nb * 3 * UT_WP_B), mbar);
   }
   if (warp == 0) tmem_alloc(slot, (uint32_t)g.tmem_cols);
-  cp_async_wait_all();
   fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
+  mbar_wait(mbar, 0);     // phase 0 is spent on the weights: the MMA phases of the kernels start at parity 1
   return *slot;
 }
 
@@ -482,7 +481,7 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_fwd_tc_kernel(UnitFwdParams q, 
   const ImgThread itx = img_thread(g, q.x, lane);
   const XmuThread xth = xmu_thread(etab, K * ((K + 1) / 2), tid);
   float xv[4][4];
-  uint32_t phase = 0;
+  uint32_t phase = 1;
   bool ok = true;
   if ((long long)blockIdx.x < nitems) {
     const int n = (int)(blockIdx.x / nchunk), p0 = (int)(blockIdx.x - (long long)n * nchunk) * g.F;
@@ -624,7 +623,7 @@ __global__ void __launch_bounds__(UT_NT, 1) unit_bwd_tc_kernel(UnitBwdParams q, 
   const XmuThread xth = xmu_thread(etab, K * ((K + 1) / 2), tid);
   float xv[4][4], gv[4][4];
   float accb[DSTD_MAX_BRANCH] = {0.f, 0.f};
-  uint32_t phase = 0;
+  uint32_t phase = 1;
   bool ok = true;
   if ((long long)blockIdx.x < nitems) {
     const int n = (int)(blockIdx.x / nchunk), p0 = (int)(blockIdx.x - (long long)n * nchunk) * g.F;
