@@ -625,10 +625,15 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bytes_pass = algorithmic_bytes_per_pass(v, t, feat(args.workload))
-        traffic = None      # measured DRAM bytes per step (ncu dram__bytes_read+write over every launch of one step)
-        tpath = os.path.join(ROOT, "profiles", f"r01_dram_traffic_{args.workload}_b{args.batch}.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+        # DRAM bytes per step as MEASURED EARLIER with ncu (dram__bytes_read+write over every launch of one step) and
+        # committed under profiles/: a static figure, not re-measured by this run (traffic_source says which file)
+        traffic, traffic_src = None, None
+        for rr in ("r02", "r01"):
+            tpath = os.path.join(ROOT, "profiles", f"{rr}_dram_traffic_{args.workload}_b{args.batch}.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+                traffic_src = f"profiles/{os.path.basename(tpath)} (static: measured with ncu in an earlier run)"
+                break
         passes_per_s_gpu = 2.0 * sps / world                      # inverse=True: two model passes per sample
         achieved = passes_per_s_gpu * bytes_pass / 1e9
         h2d = sum(x.numel() * 4 for x in host[0])
@@ -642,7 +647,7 @@ def main():
             "gpu_launches": launches, "cuda_graph": not args.no_graph,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": 2 * bytes_pass * args.batch,
                          "scope": "whole training step per GPU: algorithmic bytes = one HBM round trip per DSTDGCB "
                                   f"layer fwd+bwd = {bytes_pass} B per model pass (SURVEY.md 8d), 2 passes per sample",
