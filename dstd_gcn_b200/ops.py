@@ -255,13 +255,69 @@ FUSE_SKIP_GRAD = os.environ.get("DSTD_FUSE_SKIP_GRAD", "1") not in ("", "0")
 FUSE_RES_GRAD = os.environ.get("DSTD_FUSE_RES_GRAD", "0") not in ("", "0")
 
 
+# When a list, training-mode BatchNorm calls do NOT update their running statistics in the kernel; they append
+# [running_mean, running_var, num_batches_tracked, momentum, eps, count, save_mean, save_invstd] instead and the caller
+# applies the updates later with `apply_deferred_bn_updates` (engine.TrainStep runs the two passes of a step on two
+# streams; the reference updates the statistics of the time-reversed pass AFTER those of the forward pass).
+_bn_defer = None
+
+
+class defer_bn_updates:
+    """Context manager: collect the running-statistics updates of every BatchNorm call inside it."""
+
+    def __init__(self):
+        self.items = []
+
+    def __enter__(self):
+        global _bn_defer
+        self._prev, _bn_defer = _bn_defer, self.items
+        return self.items
+
+    def __exit__(self, *exc):
+        global _bn_defer
+        _bn_defer = self._prev
+        return False
+
+
+@torch.no_grad()
+def apply_deferred_bn_updates(items):
+    """running = (1 - momentum) * running + momentum * batch statistic (unbiased variance), num_batches_tracked += 1
+    (torch.nn.BatchNorm1d semantics, model/dstdgcn.py:42-49) for every collected call, in a handful of foreach kernels."""
+    if not items:
+        return
+    groups = {}
+    for rm, rv, nbt, mom, eps, cnt, mean, invstd in items:
+        groups.setdefault((mom, eps, cnt), []).append((rm, rv, nbt, mean, invstd))
+    for (mom, eps, cnt), g in groups.items():
+        rms, rvs = [e[0] for e in g], [e[1] for e in g]
+        nbts = [e[2] for e in g if e[2] is not None]
+        means, invs = [e[3] for e in g], [e[4] for e in g]
+        torch._foreach_mul_(rms, 1.0 - mom)
+        torch._foreach_add_(rms, means, alpha=mom)
+        var = torch._foreach_mul(invs, invs)
+        torch._foreach_reciprocal_(var)                 # biased variance + eps
+        torch._foreach_sub_(var, eps)
+        torch._foreach_mul_(var, mom * (cnt / max(cnt - 1.0, 1.0)))
+        torch._foreach_mul_(rvs, 1.0 - mom)
+        torch._foreach_add_(rvs, var)
+        if nbts:
+            torch._foreach_add_(nbts, 1)
+
+
 class _BnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, r, gamma, beta, prelu, running_mean, running_var, nbt, mask, out_order, vc_order, training,
                 eps, momentum, pass_r):
+        deferred = _bn_defer is not None and training and running_mean is not None
+        if deferred:
+            n, _, t, _ = y.shape
+            entry = [running_mean, running_var, nbt, float(momentum), float(eps), float(n * t)]
+            running_mean = running_var = nbt = None
         out, mean, invstd = torch.ops.dstd_b200.bn_act_fwd(y, r, gamma, beta, running_mean, running_var, nbt, prelu,
                                                            mask, out_order, vc_order, training, eps, momentum)
+        if deferred:
+            _bn_defer.append(entry + [mean, invstd])
         ctx.save_for_backward(y, r, gamma, beta, prelu, mask, mean, invstd)
         ctx.vc_order, ctx.training, ctx.pass_r = vc_order, training, pass_r
         if pass_r:

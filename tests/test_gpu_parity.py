@@ -732,6 +732,31 @@ def test_cuda_graph_step_matches_eager():
 
 
 # ================================================================================================= edge cases
+def test_two_stream_passes_match_sequential(monkeypatch):
+    """TrainStep runs the forward and the time-reversed pass on two streams by default; DSTD_OVERLAP_PASSES=0 runs them
+    one after the other.  Same kernels, same gradient sum: the parameters must agree bit for bit after several steps,
+    the BatchNorm running statistics (updated after the join for the second pass) to rounding."""
+    from dstd_gcn_b200.engine import TrainStep
+    import bench
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DSTD_OVERLAP_PASSES", flag)
+        torch.manual_seed(5)
+        m = _perturbed(_mod("std").DSTDGCN(6, 10, 25, 0.0, 22, 16, 2, "h36m")).to(DEV).train()
+        step = TrainStep(m, lr=3e-3, inverse=True)
+        assert step._overlap == (flag == "1")
+        for s_ in range(3):
+            step(*(x.to(DEV) for x in bench.synthetic_batch(8, 35, 22, 10, seed=40 + s_)))
+        torch.cuda.synchronize()
+        res.append((step.flat.param.clone(), {k: b.clone() for k, b in m.named_buffers()}))
+    assert torch.equal(res[0][0], res[1][0])
+    for k, b in res[0][1].items():
+        if b.is_floating_point():
+            assert max_abs(b, res[1][1][k]) < 1e-5 * max(1.0, float(res[1][1][k].abs().max())), k
+        else:
+            assert torch.equal(b, res[1][1][k]), k
+
+
 def test_batch_of_one_and_non_contiguous_input():
     """N=1 (BatchNorm statistics over T only) and a strided input tensor, against the oracle."""
     from oracle import dstd_oracle as orc

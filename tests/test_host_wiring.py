@@ -171,3 +171,25 @@ def test_registry_and_errors():
         Graph("nope")
     with pytest.raises(NotImplementedError):
         std.DSTDGC(4, 4, 5, 5, red_channels=3)            # the kernels implement the reference's red_channels=2
+
+
+def test_deferred_bn_updates_match_torch_batchnorm():
+    """`ops.apply_deferred_bn_updates` (the running-statistics update of the second, concurrently running pass of a
+    training step) against torch.nn.BatchNorm1d applied to the same two batches in order."""
+    import torch
+    from dstd_gcn_b200 import ops
+    torch.manual_seed(0)
+    c, n, t = 12, 6, 9
+    bn = torch.nn.BatchNorm1d(c).double().train()
+    ref = torch.nn.BatchNorm1d(c).double().train()
+    xa, xb = torch.randn(n, c, t, dtype=torch.float64) * 3 + 1, torch.randn(n, c, t, dtype=torch.float64) * 0.5 - 2
+    ref(xa)
+    ref(xb)
+    bn(xa)                                                     # first pass: updated in place
+    mean = xb.mean(dim=(0, 2))
+    invstd = 1.0 / torch.sqrt(xb.var(dim=(0, 2), unbiased=False) + bn.eps)
+    ops.apply_deferred_bn_updates([[bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps,
+                                    float(n * t), mean, invstd]])
+    assert torch.allclose(bn.running_mean, ref.running_mean, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(bn.running_var, ref.running_var, rtol=1e-10, atol=1e-12)
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 2

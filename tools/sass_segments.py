@@ -13,9 +13,11 @@ def analyze(path):
     hdr = rows[0]
     data = [r for r in rows[1:] if r[0] != hdr[0]]          # one kernel per file (filter with --kernel-name)
     si = hdr.index('# Samples')
+    ii = hdr.index('Instructions Executed')
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
     tot = sum(int(r[si]) for r in data)
-    print('total samples', tot, 'instructions', len(data))
+    itot = sum(int(r[ii]) for r in data)
+    print('total samples', tot, 'SASS instructions', len(data), 'executed warp instructions', itot)
     seg, cur, start = [], 0, 0
     for idx, r in enumerate(data):
         cur += int(r[si])
@@ -37,7 +39,8 @@ def analyze(path):
             kinds[op] = kinds.get(op, 0) + int(r[si])
         top = sorted(agg.items(), key=lambda x: -x[1])[:4]
         topk = sorted(kinds.items(), key=lambda x: -x[1])[:6]
-        print(f"  instr {s[0]:5d}-{s[1]:5d}: {100 * s[2] / tot:5.1f}%  stalls {top}  ops {topk}")
+        iex = sum(int(r[ii]) for r in data[s[0]:s[1] + 1])
+        print(f"  instr {s[0]:5d}-{s[1]:5d}: {100 * s[2] / tot:5.1f}% of samples, {100 * iex / itot:5.1f}% of executed instructions  stalls {top}  ops {topk}")
 
 
 if __name__ == '__main__':
