@@ -44,3 +44,39 @@ def test_mirror_h36m_matches_reference():
     got = data.mirror_h36m(torch.from_numpy(a))
     assert np.array_equal(got.numpy(), m.reshape(3, 7, 96))
     assert np.array_equal(data.mirror_h36m(got).numpy(), a)      # an involution
+
+
+def _ref_mirror(a, right, left):
+    n, t, vc = a.shape
+    m = a.copy().reshape(n, t, vc // 3, 3)
+    src = a.reshape(n, t, vc // 3, 3)
+    m[:, :, right] = src[:, :, left]          # dataset/cmu.py:99-101, dataset/pw3d.py:123-125
+    m[:, :, left] = src[:, :, right]
+    m[..., 0] = -m[..., 0]
+    return m.reshape(n, t, vc)
+
+
+def test_mirror_cmu_and_3dpw_match_reference():
+    rng = np.random.default_rng(7)
+    cmu = rng.standard_normal((3, 6, 38 * 3)).astype(np.float32)
+    got = data.mirror(torch.from_numpy(cmu), "cmu")
+    ref = _ref_mirror(cmu, [2, 3, 4, 5, 6, 21, 22, 23, 24, 27, 25, 26, 28], [8, 9, 10, 11, 12, 30, 31, 32, 33, 36, 24, 35, 37])
+    assert np.array_equal(got.numpy(), ref)
+    pw = rng.standard_normal((2, 5, 24 * 3)).astype(np.float32)
+    got = data.mirror(torch.from_numpy(pw), "3dpw")
+    ref = _ref_mirror(pw, [1, 4, 7, 10, 13, 16, 18, 20, 22], [2, 5, 8, 11, 14, 17, 19, 21, 23])
+    assert np.array_equal(got.numpy(), ref)
+    assert np.array_equal(data.mirror(got, "3dpw").numpy(), pw)     # a clean permutation: an involution
+
+
+def test_prefetcher_yields_reference_tuples_in_order_on_cpu():
+    rng = np.random.default_rng(9)
+    raws = [rng.standard_normal((4, 35, 96)).astype(np.float32) for _ in range(5)]
+    dim_used = np.arange(0, 66)
+    out = list(data.DevicePrefetcher(raws, 10, 25, dim_used, device="cpu", mirror_layout="h36m"))
+    assert len(out) == 5
+    for raw, (a, b, c, seqs) in zip(raws, out):
+        full = np.concatenate((raw, _ref_mirror(raw, data._H36M_RIGHT, data._H36M_LEFT)), axis=0)
+        ra, rb, rc = _ref_windows(full, 10, 25, dim_used, True)
+        assert np.array_equal(seqs.numpy(), full)
+        assert np.array_equal(a.numpy(), ra) and np.array_equal(b.numpy(), rb) and np.array_equal(c.numpy(), rc)

@@ -757,6 +757,28 @@ def test_two_stream_passes_match_sequential(monkeypatch):
             assert torch.equal(b, res[1][1][k]), k
 
 
+def test_prefetcher_feeds_the_device_path():
+    """`data.DevicePrefetcher`: pinned double-buffered H2D on a side stream + device-side window gathers give the same
+    tuples as the host construction, in order, and train a step."""
+    import numpy as np
+    from dstd_gcn_b200 import data
+    from dstd_gcn_b200.engine import TrainStep
+    rng = np.random.default_rng(11)
+    raws = [rng.standard_normal((6, 35, 96)).astype(np.float32) for _ in range(4)]
+    dim_used = np.arange(0, 66)
+    host = list(data.DevicePrefetcher(raws, 10, 25, dim_used, device="cpu", mirror_layout="h36m"))
+    torch.manual_seed(2)
+    m = _perturbed(_mod("std").DSTDGCN(6, 10, 25, 0.0, 22, 8, 1, "h36m")).to(DEV).train()
+    step = TrainStep(m, lr=1e-3, inverse=True)
+    n = 0
+    for (a, b, c, s_), (ha, hb, hc, hs) in zip(data.DevicePrefetcher(raws, 10, 25, dim_used, device=DEV, mirror_layout="h36m"), host):
+        assert a.is_cuda and torch.equal(a.cpu(), ha) and torch.equal(b.cpu(), hb) and torch.equal(c.cpu(), hc)
+        assert torch.equal(s_.cpu(), hs)
+        assert torch.isfinite(step(a.contiguous(), b.contiguous(), c.contiguous()))
+        n += 1
+    assert n == 4
+
+
 def test_batch_of_one_and_non_contiguous_input():
     """N=1 (BatchNorm statistics over T only) and a strided input tensor, against the oracle."""
     from oracle import dstd_oracle as orc
