@@ -318,6 +318,43 @@ def time_gpu_eager_reference(workload, batch, steps, warmup):
                     "batches from pinned host memory, loss.item() every step as the reference does"}
 
 
+def time_gpu_eager_inference(args, ours, host, dev):
+    """Eval-mode forward of the unmodified reference module (baseline/_ref, same variant) on the same B200 with OUR
+    model's weights and running statistics (so both compute the same function), torch eager fp32, no_grad."""
+    import importlib
+    import torch
+    if load_reference() is None:
+        return None
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mod = importlib.import_module("model.dstdgcn_fast" if args.variant == "dstdgcn_fast" else "model.dstdgcn")
+    layout, v, t_in, t_out, drop = WORKLOADS[args.workload]
+    ref = mod.DSTDGCN(6, t_in, t_out, drop, v, feat(args.workload), N_LAYERS, layout)
+    for p in ref.parameters():
+        p.data = p.data.clone()
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref = ref.to(dev).eval()
+    xs = [h.to(dev) for h in host]
+    with torch.no_grad():
+        y = ref(xs[0])
+        for _ in range(2):
+            ref(xs[1])
+        torch.cuda.synchronize()
+        k = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            ref(xs[i % len(xs)])
+        e1.record()
+        torch.cuda.synchronize()
+        mine = ours(xs[0])
+    ms = e0.elapsed_time(e1) / k
+    return {"value": args.batch / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": k,
+            "max_abs_diff_vs_this_path": float((mine - y).abs().max()), "output_scale": float(y.abs().max()),
+            "what": f"unmodified reference {mod.__name__}.DSTDGCN (baseline/_ref), eval forward, torch eager fp32 (TF32 off), "
+                    f"batch {args.batch}, same weights and running statistics"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -424,6 +461,12 @@ def run_infer(args, model, be, dev, rank, world, t, v, t_in):
         cfg = workload_config(args)
         cfg["workload"] = cfg["workload"].replace("training step with inverse pass", "eval-mode forward (BN on running stats)")
         cfg["variant"] = args.variant
+        eager = None
+        if not args.no_gpu_eager_baseline:
+            try:
+                eager = time_gpu_eager_inference(args, model, host, dev)
+            except Exception as e:
+                eager = {"error": repr(e)}
         print(json.dumps({
             "metric": "infer_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -433,6 +476,7 @@ def run_infer(args, model, be, dev, rank, world, t, v, t_in):
             "gpu_launches": launches_per_step * args.steps, "cuda_graph": True, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "scope": f"forward only: {bytes_fwd} algorithmic B per sample (SURVEY.md 8d)"},
+            "gpu_eager_baseline": eager,
         }), flush=True)
     if world > 1:
         shutdown(dist, torch)
