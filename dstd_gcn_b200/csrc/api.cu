@@ -136,7 +136,9 @@ static size_t gc_fwd_ws(int Cin, int Cout, int nb, int P = 40, int K = 40) {
 }
 // shapes beyond the specialised tiles (P or K > 40) run the shape-generic kernels of generic.cu
 static bool use_generic(int Cin, int P, int K) { return !(dynadj_supported(P, K) && aggregate_supported(Cin, P, K)); }
-static int dyn_splits(int N, int nb, int Cin, int P, int K) { return use_generic(Cin, P, K) ? N : dynadj_bwd_splits(N, nb); }
+static int dyn_splits(int N, int nb, int Cin, int P, int K) {
+  return use_generic(Cin, P, K) ? N * dynadj_gen_tiles(K) : dynadj_bwd_splits(N, nb);
+}
 // per-CTA partial slots of the persistent kernels (one or two per SM)
 static size_t part_slots() { return (size_t)2 * num_sms(); }
 static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
@@ -147,7 +149,8 @@ static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
                      G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, ((size_t)S1 > ps ? (size_t)S1 : ps) * 4 * nb * C1 * 4,
                      (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4,
-                     ps * nb * Cout * Cin * 4, ps * nb * Cout * 4, unit_tc_ws_bytes(nb)});
+                     ps * nb * Cout * Cin * 4, ps * nb * Cout * 4, unit_tc_ws_bytes(nb),
+                     use_generic(Cin, P, K) ? dynadj_bwd_gen_ws_floats(N, nb, P, K) * 4 : 0});
 }
 
 static int gc_check_common(int N, int Cin, int Cout, int P, int K, int nb, const dstd_branch* br, const char* fn) {
@@ -342,6 +345,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   float* p_wf = ar.take<float>(ps * nb * Cout * Cin);
   float* p_bf = ar.take<float>(ps * nb * Cout);
   void* wunit = ar.take<char>(unit_tc_ws_bytes(nb));
+  float* gm2_part = ar.take<float>(generic ? dynadj_bwd_gen_ws_floats(N, nb, P, K) : 0);
 
   PackParams pk;
   fill_pack(pk, Cin, Cout, nb, a->br, wcat, wm);
@@ -409,7 +413,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
     db.b_rm[b] = a->br[b < nb ? b : 0].b_rm;
   }
   db.S = S2; db.part_wrm = p_wrm; db.part_adj = p_adj; db.part_alpha = p_alpha;
-  if ((rc = generic ? launch_dynadj_bwd_gen(db, st) : launch_dynadj_bwd(db, st))) return rc;
+  if ((rc = generic ? launch_dynadj_bwd_gen(db, gm2_part, st) : launch_dynadj_bwd(db, st))) return rc;
 
   // 5+6. gx += wm^T gm ; g(wm)[j, c] = sum gm[j] [x;1][c]   (one pass over x)
   int S1b = 0;
@@ -466,7 +470,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
     seg(p_wrm + (long long)b * P * P21, S2, (long long)nb * P * P21, P, 2 * P, P21, g.w_rm, 2 * P);
     seg(p_wrm + (long long)b * P * P21 + 2 * P, S2, (long long)nb * P * P21, P, 1, P21, g.b_rm, 1);
     float* gadjw = a->br[b].adj_w ? g.adj_w : nullptr;
-    seg(p_adj + (long long)b * K * K, S2, (long long)nb * K * K, K, K, K, g.adj_eff, K, a->br[b].adj, gadjw);
+    seg(p_adj + (long long)b * K * K, generic ? N : S2, (long long)nb * K * K, K, K, K, g.adj_eff, K, a->br[b].adj, gadjw);
   }
   seg(p_alpha, S2 * nb, 1, 1, 1, 1, a->alpha ? a->galpha : nullptr, 1);
   return launch_reduce(rp, st);

@@ -73,140 +73,148 @@ int launch_dynadj_fwd_gen(const DynAdjFwdParams& q, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ dynamic adjacency, backward
-// CTA = (n, b), walking tiles of VT whole rows v (all w).  With gP = alpha * gxm:
+// CTA = (b, n, tile of VT whole rows v with all their w).  With gP = alpha * gxm:
 //   gD[k'][e] = sum_p Wrm[p][k'] gP[p][e] ;  gS = gD (1 - D^2)
-//   gm1[r,p',v] = sum_w gS[(r,p'),v,w]      gm2[r,p',w] = - sum_v gS[(r,p'),v,w]      (accumulated over the v tiles)
-//   gWrm[p][k'] += sum_e gP[p][e] D[k'][e]  gbrm[p] += sum_e gP[p][e]                 -> partial slot n (already x alpha)
-//   gA_eff[e]    = sum_p gxm[p][e]          galpha += sum gxm pd                       -> partial slot n
+//   gm1[r,p',v] = sum_w gS[(r,p'),v,w]                                       complete inside the tile -> gm
+//   gm2[r,p',w] = - sum_v gS[(r,p'),v,w]                                     partial per tile -> gm2_part, summed below
+//   gWrm[p][k'] = sum_e gP[p][e] D[k'][e]   gbrm[p] = sum_e gP[p][e]         -> partial slot (n, tile) (already x alpha)
+//   gA_eff[e]   = sum_p gxm[p][e]                                            -> slot n (the tiles own disjoint e ranges)
+//   galpha      = sum gxm pd                                                 -> partial slot (n, tile)
 constexpr int DB_KC = 16, DB_TP = 128;
 
-__global__ void __launch_bounds__(256) dynadj_bwd_gen_kernel(DynAdjBwdParams q) {
+int dynadj_gen_tiles(int K) {
+  const int VT = DB_TP / K > 0 ? DB_TP / K : 1;
+  return (K + VT - 1) / VT;
+}
+
+__global__ void __launch_bounds__(256) dynadj_bwd_gen_kernel(DynAdjBwdParams q, float* __restrict__ gm2_part, int NT) {
   extern __shared__ __align__(16) float smem[];
   const int P = q.P, K = q.K, KK = K * K, P2 = 2 * P, P21 = P2 + 1;
-  const int VT = max(1, DB_TP / K), TP = VT * K;          // K <= 128: at least one row per tile
+  const int VT = max(1, DB_TP / K);                       // K <= 128: at least one row per tile
   constexpr int GLD = DB_TP + 1;
   float* gPs = smem;                         // [P][GLD]
   float* Ds = gPs + P * GLD;                 // [DB_KC][DB_TP]
   float* Gs = Ds + DB_KC * DB_TP;            // [DB_KC][DB_TP]
-  float* acc2 = Gs + DB_KC * DB_TP;          // [2P][K]
-  float* gb = acc2 + P2 * K;                 // [P]
-  float* red = gb + ((P + 3) & ~3);          // [32]
+  float* red = Gs + DB_KC * DB_TP;           // [32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x, n = blockIdx.y;
+  const int b = blockIdx.x, n = blockIdx.y, tile = blockIdx.z;
+  const int v0 = tile * VT, vt = min(VT, K - v0), tp = vt * K, e0 = v0 * K;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
   const float* mb = q.m + (long long)(n * q.nb + b) * 4 * P * K;
   const float* gx = q.gxm + (long long)(n * q.nb + b) * P * KK;
   const float* pdb = q.pd + (long long)(n * q.nb + b) * P * KK;
   const float* wrm = q.w_rm[b];
   float* gmb = q.gm + (long long)(n * q.nb + b) * 4 * P * K;
-  float* pw = q.part_wrm + ((long long)n * q.nb + b) * P * P21;
+  const long long slot = ((long long)n * NT + tile) * q.nb + b;
+  float* pw = q.part_wrm + slot * P * P21;
   float* pa = q.part_adj + ((long long)n * q.nb + b) * KK;
-  for (int i = tid; i < P2 * K; i += 256) acc2[i] = 0.f;
-  for (int i = tid; i < P; i += 256) gb[i] = 0.f;
-  for (int i = tid; i < P * P21; i += 256) pw[i] = 0.f;
+  float* g2 = gm2_part + (((long long)(n * q.nb + b)) * NT + tile) * P2 * K;
   float ga = 0.f;
-  __syncthreads();
 
-  for (int v0 = 0; v0 < K; v0 += VT) {
-    const int vt = min(VT, K - v0), tp = vt * K, e0 = v0 * K;
-    // a. gP tile, static-adjacency gradient, alpha gradient
-    for (int i = tid; i < P * TP; i += 256) {
-      const int p = i / TP, e = i - p * TP;
-      float g = 0.f;
-      if (e < tp) {
-        g = __ldg(gx + (long long)p * KK + e0 + e);
-        ga = fmaf(g, __ldg(pdb + (long long)p * KK + e0 + e), ga);
+  // a. gP tile, alpha gradient
+  for (int i = tid; i < P * tp; i += 256) {
+    const int p = i / tp, e = i - p * tp;
+    const float g = __ldg(gx + (long long)p * KK + e0 + e);
+    ga = fmaf(g, __ldg(pdb + (long long)p * KK + e0 + e), ga);
+    gPs[p * GLD + e] = alpha * g;
+  }
+  __syncthreads();
+  for (int e = tid; e < tp; e += 256) {          // static-adjacency gradient: the raw sum (alpha may be 0)
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += __ldg(gx + (long long)p * KK + e0 + e);
+    pa[e0 + e] = s;
+  }
+  for (int p = warp; p < P; p += 8) {            // conv_rm bias gradient: row sums (fixed order: lanes then butterfly)
+    float s = 0.f;
+    for (int e = lane; e < tp; e += 32) s += gPs[p * GLD + e];
+    s = warp_sum(s);
+    if (lane == 0) pw[(long long)p * P21 + P2] = s;
+  }
+  for (int k0 = 0; k0 < P2; k0 += DB_KC) {
+    // b. D chunk
+    for (int i = tid; i < DB_KC * tp; i += 256) {
+      const int kk = i / tp, e = i - kk * tp, kp = k0 + kk;
+      float d = 0.f;
+      if (kp < P2) {
+        const int r = kp / P, pp = kp - r * P, vl = e / K, w = e - vl * K;
+        d = fast_tanh(__ldg(mb + (r * P + pp) * K + v0 + vl) - __ldg(mb + ((2 + r) * P + pp) * K + w));
       }
-      gPs[p * GLD + e] = alpha * g;
+      Ds[kk * DB_TP + e] = d;
     }
     __syncthreads();
-    for (int e = tid; e < tp; e += 256) {          // static-adjacency gradient: the raw sum (alpha may be 0)
+    // c. gS = (Wrm^T gP) (1 - D^2)
+    for (int i = tid; i < DB_KC * tp; i += 256) {
+      const int kk = i / tp, e = i - kk * tp, kp = k0 + kk;
       float s = 0.f;
-      for (int p = 0; p < P; ++p) s += __ldg(gx + (long long)p * KK + e0 + e);
-      pa[e0 + e] = s;
-    }
-    for (int p = warp; p < P; p += 8) {          // conv_rm bias gradient: row sums (fixed order: lanes then butterfly)
-      float s = 0.f;
-      for (int e = lane; e < tp; e += 32) s += gPs[p * GLD + e];
-      s = warp_sum(s);
-      if (lane == 0) gb[p] += s;
-    }
-    for (int k0 = 0; k0 < P2; k0 += DB_KC) {
-      // b. D chunk
-      for (int i = tid; i < DB_KC * TP; i += 256) {
-        const int kk = i / TP, e = i - kk * TP, kp = k0 + kk;
-        float d = 0.f;
-        if (kp < P2 && e < tp) {
-          const int r = kp / P, pp = kp - r * P, vl = e / K, w = e - vl * K;
-          d = fast_tanh(__ldg(mb + (r * P + pp) * K + v0 + vl) - __ldg(mb + ((2 + r) * P + pp) * K + w));
-        }
-        Ds[kk * DB_TP + e] = d;
+      if (kp < P2) {
+        for (int p = 0; p < P; ++p) s = fmaf(__ldg(wrm + (long long)p * P2 + kp), gPs[p * GLD + e], s);
+        const float d = Ds[kk * DB_TP + e];
+        s *= 1.f - d * d;
       }
-      __syncthreads();
-      // c. gS = (Wrm^T gP) (1 - D^2)
-      for (int i = tid; i < DB_KC * TP; i += 256) {
-        const int kk = i / TP, e = i - kk * TP, kp = k0 + kk;
+      Gs[kk * DB_TP + e] = s;
+    }
+    // d. gWrm[p][k'] = sum_e gP[p][e] D[k'][e]   (lanes = p: the GLD = 129 pitch keeps the row reads conflict free)
+    for (int i = tid; i < DB_KC * P; i += 256) {
+      const int kk = i / P, p = i - kk * P, kp = k0 + kk;
+      if (kp < P2) {
         float s = 0.f;
-        if (kp < P2 && e < tp) {
-          for (int p = 0; p < P; ++p) s = fmaf(__ldg(wrm + (long long)p * P2 + kp), gPs[p * GLD + e], s);
-          const float d = Ds[kk * DB_TP + e];
-          s *= 1.f - d * d;
-        }
-        Gs[kk * DB_TP + e] = s;
+        for (int e = 0; e < tp; ++e) s = fmaf(gPs[p * GLD + e], Ds[kk * DB_TP + e], s);
+        pw[(long long)p * P21 + kp] = s;
       }
-      // d. gWrm[p][k'] += sum_e gP[p][e] D[k'][e]   (lanes = p: the GLD = 129 pitch keeps the row reads conflict free)
-      for (int i = tid; i < DB_KC * P; i += 256) {
-        const int kk = i / P, p = i - kk * P, kp = k0 + kk;
-        if (kp < P2) {
-          float s = 0.f;
-          for (int e = 0; e < tp; ++e) s = fmaf(gPs[p * GLD + e], Ds[kk * DB_TP + e], s);
-          pw[(long long)p * P21 + kp] += s;
-        }
-      }
-      __syncthreads();
-      // e. row / column sums of gS
-      for (int i = tid; i < DB_KC * vt; i += 256) {
-        const int kk = i / vt, vl = i - kk * vt, kp = k0 + kk;
-        if (kp < P2) {
-          float s = 0.f;
-          for (int w = 0; w < K; ++w) s += Gs[kk * DB_TP + vl * K + w];
-          const int r = kp / P, pp = kp - r * P;
-          gmb[(r * P + pp) * K + v0 + vl] = s;
-        }
-      }
-      for (int i = tid; i < DB_KC * K; i += 256) {
-        const int kk = i / K, w = i - kk * K, kp = k0 + kk;
-        if (kp < P2) {
-          float s = 0.f;
-          for (int vl = 0; vl < vt; ++vl) s += Gs[kk * DB_TP + vl * K + w];
-          acc2[kp * K + w] += s;
-        }
-      }
-      __syncthreads();
     }
+    __syncthreads();
+    // e. row / column sums of gS
+    for (int i = tid; i < DB_KC * vt; i += 256) {
+      const int kk = i / vt, vl = i - kk * vt, kp = k0 + kk;
+      if (kp < P2) {
+        float s = 0.f;
+        for (int w = 0; w < K; ++w) s += Gs[kk * DB_TP + vl * K + w];
+        const int r = kp / P, pp = kp - r * P;
+        gmb[(r * P + pp) * K + v0 + vl] = s;
+      }
+    }
+    for (int i = tid; i < DB_KC * K; i += 256) {
+      const int kk = i / K, w = i - kk * K, kp = k0 + kk;
+      if (kp < P2) {
+        float s = 0.f;
+        for (int vl = 0; vl < vt; ++vl) s += Gs[kk * DB_TP + vl * K + w];
+        g2[kp * K + w] = s;
+      }
+    }
+    __syncthreads();
   }
-  for (int i = tid; i < P2 * K; i += 256) {
-    const int kp = i / K, w = i - kp * K, r = kp / P, pp = kp - r * P;
-    gmb[((2 + r) * P + pp) * K + w] = -acc2[i];
-  }
-  for (int p = tid; p < P; p += 256) pw[(long long)p * P21 + P2] = gb[p];
   ga = block_sum(ga, red);
-  if (tid == 0) q.part_alpha[n * q.nb + b] = ga;
+  if (tid == 0) q.part_alpha[slot] = ga;
 }
 
-static size_t dynadj_bwd_gen_smem(int P, int K) {
-  return ((size_t)P * (DB_TP + 1) + 2 * DB_KC * DB_TP + (size_t)2 * P * K + ((P + 3) & ~3) + 32) * sizeof(float);
+// gm2[n,b,r,p',w] = - sum over the v tiles of the partial column sums (fixed order)
+__global__ void gm2_reduce_kernel(const float* __restrict__ gm2_part, float* __restrict__ gm, int NB, int NT, int P, int K) {
+  const long long per = (long long)2 * P * K, total = (long long)NB * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long nb_ = i / per, r = i - nb_ * per;
+    const float* src = gm2_part + nb_ * NT * per + r;
+    float s = 0.f;
+    for (int t = 0; t < NT; ++t) s += src[t * per];
+    gm[nb_ * 2 * per + per + r] = -s;
+  }
 }
 
-int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, cudaStream_t st) {
+size_t dynadj_bwd_gen_ws_floats(int N, int nb, int P, int K) { return (size_t)N * nb * dynadj_gen_tiles(K) * 2 * P * K; }
+
+int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, float* gm2_part, cudaStream_t st) {
   DSTD_REQUIRE(generic_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED, "dynadj_bwd_gen: P=%d K=%d outside limits (<= %d)", q.P, q.K, GEN_MAX);
-  DSTD_REQUIRE(q.S == q.N, DSTD_ERR_BAD_ARG, "dynadj_bwd_gen: one partial slot per sample expected");
-  const size_t smem = dynadj_bwd_gen_smem(q.P, q.K);
+  const int NT = dynadj_gen_tiles(q.K);
+  DSTD_REQUIRE(q.S == q.N * NT && gm2_part, DSTD_ERR_BAD_ARG, "dynadj_bwd_gen: one partial slot per (sample, tile) expected");
+  const size_t smem = ((size_t)q.P * (DB_TP + 1) + 2 * DB_KC * DB_TP + 32) * sizeof(float);
   ensure_max_smem((const void*)dynadj_bwd_gen_kernel);
-  dim3 grid(q.nb, q.N);
-  dynadj_bwd_gen_kernel<<<grid, 256, smem, st>>>(q);
+  dim3 grid(q.nb, q.N, NT);
+  dynadj_bwd_gen_kernel<<<grid, 256, smem, st>>>(q, gm2_part, NT);
   count_launch();
-  return check_launch("dynadj_bwd_gen");
+  DSTD_LAUNCH_CHECK("dynadj_bwd_gen");
+  const long long total = (long long)q.N * q.nb * 2 * q.P * q.K;
+  gm2_reduce_kernel<<<cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184, 256, 0, st>>>(gm2_part, q.gm, q.N * q.nb, NT, q.P, q.K);
+  count_launch();
+  return check_launch("gm2_reduce");
 }
 
 // ------------------------------------------------------------------------------------------ aggregation, forward

@@ -125,7 +125,9 @@ bool aggregate_supported(int Cin, int P, int K);
 // ------------------------------------------------------------------ generic.cu (P or K > 40: the stress configuration)
 bool generic_supported(int P, int K);
 int launch_dynadj_fwd_gen(const DynAdjFwdParams& q, cudaStream_t st);
-int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, cudaStream_t st);     // q.S == q.N partial slots
+int dynadj_gen_tiles(int K);                                               // v tiles per (sample, branch)
+size_t dynadj_bwd_gen_ws_floats(int N, int nb, int P, int K);              // gm2 partials
+int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, float* gm2_part, cudaStream_t st);   // q.S == N * tiles slots; part_adj: N slots
 int launch_aggregate_fwd_gen(const AggParams& q, cudaStream_t st);
 int launch_aggregate_bwd_gen(const AggParams& q, cudaStream_t st);
 
