@@ -143,6 +143,11 @@ def _check(t, what, dtype=torch.float32):
         raise RuntimeError(f"dstd_gcn_b200: `{what}` must be a CUDA tensor (the hot path has no CPU fallback)")
     if t.dtype != dtype:
         raise RuntimeError(f"dstd_gcn_b200: `{what}` must be {dtype}, got {t.dtype}")
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        # the library launches on the CURRENT device (it never switches devices); a tensor elsewhere would be an
+        # illegal access.  One process per GPU is the supported layout: torch.cuda.set_device(local_rank) first.
+        raise RuntimeError(f"dstd_gcn_b200: `{what}` lives on cuda:{t.device.index} but the current device is "
+                           f"cuda:{torch.cuda.current_device()} (call torch.cuda.set_device first)")
 
 
 def _ptr(t):
