@@ -11,7 +11,10 @@
 // E[x^2]-E[x]^2 cancellation does not bite on millimetre-scale poses.
 #include <stdlib.h>
 
+#include <initializer_list>
+
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace dstd {
 
@@ -851,6 +854,456 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_add_kernel(BnB
   bn_bwd_apply_body<NJ, U, true>(q);
 }
 
+// ================================================================================================ fast path
+// The same three streaming passes for the case every BatchNorm of the model but the masked input one is in: no dropout
+// mask, every tensor a dense [N][C][plane] array whose CH-channel slabs (CH = 1, 2 or 4: the smallest count that makes
+// CH * T*V * 4 bytes a multiple of 16) are 16-byte aligned.  Differences from the generic kernels above:
+//  * a CTA owns CH adjacent channels and one batch split; a slab of every staged tensor arrives by ONE bulk-async copy
+//    (cp.async.bulk + mbarrier expect_tx, issued by thread 0), double buffered - the other threads spend no
+//    instruction on staging (the generic kernels spend ~20 on address arithmetic per 8-byte cp.async);
+//  * a thread keeps per owned position one packed word of shared-memory slots; the per-(c,v) constants live in a
+//    shared-memory table, outputs are walked linearly (position j of the slab in the output's own memory order);
+//  * per-element arithmetic and the order of every sum are those of the generic kernels: outputs and statistics are
+//    bit-identical (tests/test_gpu_parity.py::test_bn_fast_path_equals_generic), the PReLU-slope partial is summed
+//    over a different thread mapping (equal to rounding).
+constexpr int BNF_MAXCH = 4;
+
+__device__ __forceinline__ void bnf_decode(bool tfast, int j, int T, int V, int TV, int& ch, int& t, int& v) {
+  ch = j / TV;
+  const int jj = j - ch * TV;
+  if (tfast) {
+    v = jj / T;
+    t = jj - v * T;
+  } else {
+    t = jj / V;
+    v = jj - t * V;
+  }
+}
+__device__ __forceinline__ void bnf_timeout(int* err) {
+  if (err) *(volatile int*)err = 2;
+}
+
+// ---- forward apply: positions in out's memory order
+template <int NJ, int U, bool HAS_R, bool FULL>
+__device__ __forceinline__ void bnf_apply_consume(const float* st, const float4* ctab, const int (&pk)[NJ], float* ob,
+                                                  long long osn, int CHTV, int left, float slope) {
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    if (pk[i] >= 0) {
+      const float4 k = ctab[pk[i] >> 24];
+      const float* py = st + (pk[i] & 0xfff);
+      const float* pr = st + U * CHTV + ((pk[i] >> 12) & 0xfff);
+      float* o = ob + i * blockDim.x;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) {
+          float pre = fmaf(py[u * CHTV] - k.x, k.y, k.z);
+          if (HAS_R) pre += pr[u * CHTV];
+          o[u * osn] = pre > 0.f ? pre : slope * pre;
+        }
+      }
+    }
+  }
+}
+
+template <int NJ, int U, bool HAS_R>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_apply_kernel(BnFwdP q, int CH, int* err) {
+  extern __shared__ __align__(16) float sh[];   // [2 stages][y (, r)][U][CH * T*V]
+  __shared__ __align__(16) float4 ctab[BNF_MAXCH * 32];     // per (ch, v): mean, gamma * invstd, beta
+  __shared__ double tot[32][2];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int c0 = blockIdx.x * CH, s = blockIdx.y, T = q.T, V = q.V, TV = T * V, CHTV = CH * TV;
+  const int n0 = (int)((long long)q.N * s / gridDim.y), n1 = (int)((long long)q.N * (s + 1) / gridDim.y), cnt = n1 - n0;
+  constexpr int NST = HAS_R ? 2 : 1;
+  const int stage_f = NST * U * CHTV, iters = (cnt + U - 1) / U;
+  const float slope = q.prelu ? __ldg(q.prelu) : 1.f;
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&mbar[0], 1);
+    umma::mbar_init(&mbar[1], 1);
+    umma::mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int it) {   // thread 0: one bulk copy per sample and tensor
+    const int n = n0 + it * U, cu = min(U, n1 - n);
+    float* d = sh + (it & 1) * stage_f;
+    uint64_t* mb = &mbar[it & 1];
+    umma::mbar_expect_tx(mb, (uint32_t)(NST * cu * CHTV) * 4u);
+    const float* gy = q.y.p + (long long)n * q.y.sn + (long long)c0 * q.y.sc;
+    for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + u * CHTV, gy + u * q.y.sn, (uint32_t)CHTV * 4u, mb);
+    if (HAS_R) {
+      const float* gr = q.r.p + (long long)n * q.r.sn + (long long)c0 * q.r.sc;
+      for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + (U + u) * CHTV, gr + u * q.r.sn, (uint32_t)CHTV * 4u, mb);
+    }
+  };
+  if (threadIdx.x == 0 && iters > 0) issue(0);
+  if (q.training) {   // batch statistics from the split partials (same arithmetic as bn_apply_kernel)
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c = c0 + ch;
+      sum_partials(q.part, q.S, q.C, c, V, tot);
+      __syncthreads();
+      if (threadIdx.x < V) {
+        const int v = threadIdx.x;
+        const double cntd = (double)q.N * q.T;
+        const double shift = __ldg(q.y.p + vix(q.y, 0, c, 0, v));
+        const double dm = tot[v][0] / cntd;
+        double var = tot[v][1] / cntd - dm * dm;
+        if (var < 0.) var = 0.;
+        const double mean = shift + dm;
+        const float fm = (float)mean, fi = (float)(1.0 / sqrt(var + (double)q.eps));
+        const int pi = bn_pidx(c, v, q.C, V, q.vc_order);
+        ctab[ch * 32 + v] = make_float4(fm, __ldg(q.gamma + pi) * fi, __ldg(q.beta + pi), 0.f);
+        if (s == 0) {
+          q.save_mean[pi] = fm;
+          q.save_invstd[pi] = fi;
+          if (q.running_mean) {
+            const double unb = cntd > 1. ? var * cntd / (cntd - 1.) : var;
+            q.running_mean[pi] = (float)((1.0 - q.momentum) * q.running_mean[pi] + q.momentum * mean);
+            q.running_var[pi] = (float)((1.0 - q.momentum) * q.running_var[pi] + q.momentum * unb);
+          }
+          if (c == 0 && v == 0 && q.nbt) *q.nbt += 1;
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    if (threadIdx.x < CH * 32 && (threadIdx.x & 31) < V) {
+      const int pi = bn_pidx(c0 + (threadIdx.x >> 5), threadIdx.x & 31, q.C, V, q.vc_order);
+      ctab[threadIdx.x] = make_float4(q.save_mean[pi], __ldg(q.gamma + pi) * q.save_invstd[pi], __ldg(q.beta + pi), 0.f);
+    }
+    __syncthreads();
+  }
+  int pk[NJ];   // slot in y's slab | slot in r's slab << 12 | (ch * 32 + v) << 24
+  {
+    const bool tf_o = t_fastest(q.out), tf_y = t_fastest(q.y), tf_r = HAS_R && t_fastest(q.r);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = threadIdx.x + i * blockDim.x;
+      pk[i] = -1;
+      if (j < CHTV) {
+        int ch, t, v;
+        bnf_decode(tf_o, j, T, V, TV, ch, t, v);
+        pk[i] = (ch * TV + slot_of(tf_y, t, v, T, V)) | ((ch * TV + slot_of(tf_r, t, v, T, V)) << 12) | ((ch * 32 + v) << 24);
+      }
+    }
+  }
+  float* ob = q.out.p + (long long)n0 * q.out.sn + (long long)c0 * q.out.sc + threadIdx.x;
+  const long long osn = q.out.sn;
+  for (int it = 0; it < iters; ++it) {
+    if (threadIdx.x == 0 && it + 1 < iters) issue(it + 1);   // that buffer was released by the barrier ending it - 1
+    if (!umma::mbar_wait(&mbar[it & 1], (uint32_t)(it >> 1) & 1u)) bnf_timeout(err);
+    const float* st = sh + (it & 1) * stage_f;
+    const int left = n1 - (n0 + it * U);
+    if (left >= U) bnf_apply_consume<NJ, U, HAS_R, true>(st, ctab, pk, ob, osn, CHTV, left, slope);
+    else bnf_apply_consume<NJ, U, HAS_R, false>(st, ctab, pk, ob, osn, CHTV, left, slope);
+    ob += U * osn;
+    __syncthreads();
+  }
+}
+
+// ---- backward pass 1: positions in y's memory order
+template <int NJ, int U, bool USE_R, bool FULL>
+__device__ __forceinline__ void bnf_reduce_consume(const float* st, const float4* ctab, const int (&pk)[NJ], int CHTV,
+                                                   int left, float slope, bool has_prelu, float (&a1)[NJ],
+                                                   float (&a2)[NJ], float& gsl) {
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    if (pk[i] >= 0) {
+      const float4 k = ctab[pk[i] >> 24];
+      const float* pg = st + (pk[i] & 0xfff);
+      const float* py = st + U * CHTV + threadIdx.x + i * blockDim.x;
+      const float* pr = st + 2 * U * CHTV + ((pk[i] >> 12) & 0xfff);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) {
+          float xhat, gs;
+          const float gp = bn_gpre(has_prelu, py[u * CHTV], USE_R ? pr[u * CHTV] : 0.f, pg[u * CHTV], 1.f, k.x, k.y, k.z,
+                                   k.w, slope, xhat, gs);
+          a1[i] += gp;
+          a2[i] = fmaf(gp, xhat, a2[i]);
+          gsl += gs;
+        }
+      }
+    }
+  }
+}
+
+template <int NJ, int U, bool USE_R>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_reduce_kernel(BnBwdP q, int CH, int* err) {
+  extern __shared__ __align__(16) float sh[];   // [2 stages][gout, y (, r)][U][CH * T*V]
+  __shared__ __align__(16) float4 ctab[BNF_MAXCH * 32];     // per (ch, v): mean, invstd, gamma, beta
+  __shared__ float red[32];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int c0 = blockIdx.x * CH, s = blockIdx.y, T = q.T, V = q.V, TV = T * V, CHTV = CH * TV;
+  const int n0 = (int)((long long)q.N * s / gridDim.y), n1 = (int)((long long)q.N * (s + 1) / gridDim.y), cnt = n1 - n0;
+  constexpr int NST = USE_R ? 3 : 2;
+  const int stage_f = NST * U * CHTV, iters = (cnt + U - 1) / U;
+  const bool has_prelu = q.prelu != nullptr;
+  const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&mbar[0], 1);
+    umma::mbar_init(&mbar[1], 1);
+    umma::mbar_init_fence();
+  }
+  if (threadIdx.x < CH * 32 && (threadIdx.x & 31) < V) {
+    const int pi = bn_pidx(c0 + (threadIdx.x >> 5), threadIdx.x & 31, q.C, V, q.vc_order);
+    ctab[threadIdx.x] = make_float4(__ldg(q.save_mean + pi), __ldg(q.save_invstd + pi), __ldg(q.gamma + pi), __ldg(q.beta + pi));
+  }
+  __syncthreads();
+  auto issue = [&](int it) {
+    const int n = n0 + it * U, cu = min(U, n1 - n);
+    float* d = sh + (it & 1) * stage_f;
+    uint64_t* mb = &mbar[it & 1];
+    umma::mbar_expect_tx(mb, (uint32_t)(NST * cu * CHTV) * 4u);
+    const float* g0 = q.gout.p + (long long)n * q.gout.sn + (long long)c0 * q.gout.sc;
+    const float* g1 = q.y.p + (long long)n * q.y.sn + (long long)c0 * q.y.sc;
+    for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + u * CHTV, g0 + u * q.gout.sn, (uint32_t)CHTV * 4u, mb);
+    for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + (U + u) * CHTV, g1 + u * q.y.sn, (uint32_t)CHTV * 4u, mb);
+    if (USE_R) {
+      const float* g2 = q.r.p + (long long)n * q.r.sn + (long long)c0 * q.r.sc;
+      for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + (2 * U + u) * CHTV, g2 + u * q.r.sn, (uint32_t)CHTV * 4u, mb);
+    }
+  };
+  if (threadIdx.x == 0 && iters > 0) issue(0);
+  int pk[NJ];   // slot in gout's slab | slot in r's slab << 12 | (ch * 32 + v) << 24;  y is read at j itself
+  float a1[NJ], a2[NJ], gsl = 0.f;
+  const bool tf_y = t_fastest(q.y);
+  {
+    const bool tf_g = t_fastest(q.gout), tf_r = USE_R && t_fastest(q.r);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = threadIdx.x + i * blockDim.x;
+      pk[i] = -1;
+      a1[i] = a2[i] = 0.f;
+      if (j < CHTV) {
+        int ch, t, v;
+        bnf_decode(tf_y, j, T, V, TV, ch, t, v);
+        pk[i] = (ch * TV + slot_of(tf_g, t, v, T, V)) | ((ch * TV + slot_of(tf_r, t, v, T, V)) << 12) | ((ch * 32 + v) << 24);
+      }
+    }
+  }
+  for (int it = 0; it < iters; ++it) {
+    if (threadIdx.x == 0 && it + 1 < iters) issue(it + 1);
+    if (!umma::mbar_wait(&mbar[it & 1], (uint32_t)(it >> 1) & 1u)) bnf_timeout(err);
+    const float* st = sh + (it & 1) * stage_f;
+    const int left = n1 - (n0 + it * U);
+    if (left >= U) bnf_reduce_consume<NJ, U, USE_R, true>(st, ctab, pk, CHTV, left, slope, has_prelu, a1, a2, gsl);
+    else bnf_reduce_consume<NJ, U, USE_R, false>(st, ctab, pk, CHTV, left, slope, has_prelu, a1, a2, gsl);
+    __syncthreads();
+  }
+  // per-(c,v) totals: positions to their logical slot, then one thread per (ch, v) sums over t in order (fp64)
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < CHTV) {
+      int ch, t, v;
+      bnf_decode(tf_y, j, T, V, TV, ch, t, v);
+      sh[ch * TV + t * V + v] = a1[i];
+      sh[CHTV + ch * TV + t * V + v] = a2[i];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < CH * V; idx += blockDim.x) {
+    const int ch = idx / V, v = idx - ch * V;
+    double s1 = 0., s2 = 0.;
+    for (int t = 0; t < T; ++t) {
+      s1 += sh[ch * TV + t * V + v];
+      s2 += sh[CHTV + ch * TV + t * V + v];
+    }
+    float* dst = q.part + (((long long)s * q.C + c0 + ch) * V + v) * 2;
+    dst[0] = (float)s1;
+    dst[1] = (float)s2;
+  }
+  const float totp = block_sum(gsl, red);
+  if (threadIdx.x == 0) q.part_p[(long long)s * gridDim.x + blockIdx.x] = totp;
+}
+
+// ---- backward pass 2: positions in gy's memory order; gr (same order as gy) is stored straight from registers
+template <int NJ, int U, bool USE_R, bool HAS_GR, bool ADD, bool FULL>
+__device__ __forceinline__ void bnf_bwd_apply_consume(const float* st, const float4* ctab, const float4* ctab2,
+                                                      const int (&pk)[NJ], const int (&pk2)[NJ], float* gyb, float* grb,
+                                                      long long gysn, long long grsn, int CHTV, int left, float slope,
+                                                      bool has_prelu) {
+  constexpr int ADD_REGION = USE_R ? 3 : 2;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    if (pk[i] >= 0) {
+      const float4 k = ctab[pk[i] >> 24], k2 = ctab2[pk[i] >> 24];
+      const float* pg = st + (pk[i] & 0xfff);
+      const float* py = st + U * CHTV + ((pk[i] >> 12) & 0xfff);
+      const float* pr = st + 2 * U * CHTV + (pk2[i] & 0xfff);
+      const float* pa = st + ADD_REGION * U * CHTV + ((pk2[i] >> 12) & 0xfff);
+      float* o = gyb + i * blockDim.x;
+      float* o2 = grb + i * blockDim.x;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (FULL || u < left) {
+          float xhat, gs;
+          const float gp = bn_gpre(has_prelu, py[u * CHTV], USE_R ? pr[u * CHTV] : 0.f, pg[u * CHTV], 1.f, k.x, k.y, k.z,
+                                   k.w, slope, xhat, gs);
+          o[u * gysn] = k2.x * (gp - k2.y - xhat * k2.z);
+          if (HAS_GR) o2[u * grsn] = ADD ? gp + pa[u * CHTV] : gp;
+        }
+      }
+    }
+  }
+}
+
+template <int NJ, int U, bool USE_R, bool HAS_GR, bool ADD>
+__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_apply_kernel(BnBwdP q, int CH, int NP, int* err) {
+  extern __shared__ __align__(16) float sh[];   // [2 stages][gout, y (, r) (, gr_add)][U][CH * T*V]
+  __shared__ __align__(16) float4 ctab[BNF_MAXCH * 32];     // mean, invstd, gamma, beta
+  __shared__ __align__(16) float4 ctab2[BNF_MAXCH * 32];    // gamma * invstd, k1, k2
+  __shared__ double tot[32][2];
+  __shared__ float red[32];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int c0 = blockIdx.x * CH, s = blockIdx.y, T = q.T, V = q.V, TV = T * V, CHTV = CH * TV;
+  const int n0 = (int)((long long)q.N * s / gridDim.y), n1 = (int)((long long)q.N * (s + 1) / gridDim.y), cnt = n1 - n0;
+  constexpr int NST = 2 + (USE_R ? 1 : 0) + (ADD ? 1 : 0), ADD_REGION = USE_R ? 3 : 2;
+  const int stage_f = NST * U * CHTV, iters = (cnt + U - 1) / U;
+  const bool has_prelu = q.prelu != nullptr;
+  const float slope = has_prelu ? __ldg(q.prelu) : 1.f;
+  const float icnt = 1.0f / ((float)q.N * (float)T);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&mbar[0], 1);
+    umma::mbar_init(&mbar[1], 1);
+    umma::mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int it) {
+    const int n = n0 + it * U, cu = min(U, n1 - n);
+    float* d = sh + (it & 1) * stage_f;
+    uint64_t* mb = &mbar[it & 1];
+    umma::mbar_expect_tx(mb, (uint32_t)(NST * cu * CHTV) * 4u);
+    const float* g0 = q.gout.p + (long long)n * q.gout.sn + (long long)c0 * q.gout.sc;
+    const float* g1 = q.y.p + (long long)n * q.y.sn + (long long)c0 * q.y.sc;
+    for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + u * CHTV, g0 + u * q.gout.sn, (uint32_t)CHTV * 4u, mb);
+    for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + (U + u) * CHTV, g1 + u * q.y.sn, (uint32_t)CHTV * 4u, mb);
+    if (USE_R) {
+      const float* g2 = q.r.p + (long long)n * q.r.sn + (long long)c0 * q.r.sc;
+      for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + (2 * U + u) * CHTV, g2 + u * q.r.sn, (uint32_t)CHTV * 4u, mb);
+    }
+    if (ADD) {
+      const float* g3 = q.gadd.p + (long long)n * q.gadd.sn + (long long)c0 * q.gadd.sc;
+      for (int u = 0; u < cu; ++u) umma::bulk_g2s(d + (ADD_REGION * U + u) * CHTV, g3 + u * q.gadd.sn, (uint32_t)CHTV * 4u, mb);
+    }
+  };
+  if (threadIdx.x == 0 && iters > 0) issue(0);
+  // sums of pass 1 over the splits; the s == 0 CTA publishes the parameter gradients of its channels
+  if (blockIdx.x == 0 && s == 0 && q.gprelu) {   // fixed-order sum of the slope partials
+    float a = 0.f;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) a += q.part_p[i];
+    const float t = block_sum(a, red);
+    if (threadIdx.x == 0) q.gprelu[0] = t;
+  }
+  for (int ch = 0; ch < CH; ++ch) {
+    const int c = c0 + ch;
+    sum_partials(q.part, q.S, q.C, c, V, tot);
+    __syncthreads();
+    if (threadIdx.x < V) {
+      const int v = threadIdx.x, pi = bn_pidx(c, v, q.C, V, q.vc_order);
+      const float mu = __ldg(q.save_mean + pi), is = __ldg(q.save_invstd + pi), g = __ldg(q.gamma + pi);
+      ctab[ch * 32 + v] = make_float4(mu, is, g, __ldg(q.beta + pi));
+      ctab2[ch * 32 + v] = make_float4(g * is, q.training ? (float)tot[v][0] * icnt : 0.f,
+                                       q.training ? (float)tot[v][1] * icnt : 0.f, 0.f);
+      if (s == 0) {
+        q.gbeta[pi] = (float)tot[v][0];
+        q.ggamma[pi] = (float)tot[v][1];
+      }
+    }
+    __syncthreads();
+  }
+  int pk[NJ], pk2[NJ];   // gout slot | y slot << 12 | (ch*32+v) << 24;   r slot | gr_add slot << 12
+  {
+    const bool tf_o = t_fastest(q.gy), tf_g = t_fastest(q.gout), tf_y = t_fastest(q.y), tf_r = USE_R && t_fastest(q.r),
+               tf_a = ADD && t_fastest(q.gadd);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = threadIdx.x + i * blockDim.x;
+      pk[i] = -1;
+      pk2[i] = 0;
+      if (j < CHTV) {
+        int ch, t, v;
+        bnf_decode(tf_o, j, T, V, TV, ch, t, v);
+        pk[i] = (ch * TV + slot_of(tf_g, t, v, T, V)) | ((ch * TV + slot_of(tf_y, t, v, T, V)) << 12) | ((ch * 32 + v) << 24);
+        pk2[i] = (ch * TV + slot_of(tf_r, t, v, T, V)) | ((ch * TV + slot_of(tf_a, t, v, T, V)) << 12);
+      }
+    }
+  }
+  float* gyb = q.gy.p + (long long)n0 * q.gy.sn + (long long)c0 * q.gy.sc + threadIdx.x;
+  float* grb = HAS_GR ? q.gr.p + (long long)n0 * q.gr.sn + (long long)c0 * q.gr.sc + threadIdx.x : nullptr;
+  const long long gysn = q.gy.sn, grsn = HAS_GR ? q.gr.sn : 0;
+  for (int it = 0; it < iters; ++it) {
+    if (threadIdx.x == 0 && it + 1 < iters) issue(it + 1);
+    if (!umma::mbar_wait(&mbar[it & 1], (uint32_t)(it >> 1) & 1u)) bnf_timeout(err);
+    const float* st = sh + (it & 1) * stage_f;
+    const int left = n1 - (n0 + it * U);
+    if (left >= U)
+      bnf_bwd_apply_consume<NJ, U, USE_R, HAS_GR, ADD, true>(st, ctab, ctab2, pk, pk2, gyb, grb, gysn, grsn, CHTV, left, slope, has_prelu);
+    else
+      bnf_bwd_apply_consume<NJ, U, USE_R, HAS_GR, ADD, false>(st, ctab, ctab2, pk, pk2, gyb, grb, gysn, grsn, CHTV, left, slope, has_prelu);
+    gyb += U * gysn;
+    if (HAS_GR) grb += U * grsn;
+    __syncthreads();
+  }
+}
+
+// host side of the fast path
+struct BnFastPlan {
+  bool ok;
+  int ch, nj, threads;
+};
+static bool bnf_tfast(const View4& w) { return !(w.sk == 1 || w.sp != 1); }
+static bool bnf_slab_ok(const View4& w, int T, int V) {
+  if (!w.p) return true;
+  const bool dense = bnf_tfast(w) ? (w.sp == 1 && w.sk == T) : (w.sk == 1 && w.sp == V);
+  return dense && w.sc == (long long)T * V && (reinterpret_cast<unsigned long long>(w.p) & 15ull) == 0 && (w.sn & 3ll) == 0;
+}
+static BnFastPlan bnf_plan(int C, int T, int V, const float* mask, std::initializer_list<const View4*> ws) {
+  BnFastPlan pl{false, 0, 0, 0};
+  const char* e = getenv("DSTD_BN_FAST");          // read per call: the tests compare both paths
+  if (e && atoi(e) == 0) return pl;
+  if (mask || V > 32) return pl;
+  const int TV = T * V;
+  pl.ch = (TV % 4 == 0) ? 1 : (TV % 2 == 0) ? 2 : 4;
+  const int chtv = pl.ch * TV;
+  if (C % pl.ch || chtv > 4096) return pl;
+  for (const View4* w : ws)
+    if (!bnf_slab_ok(*w, T, V)) return pl;
+  pl.nj = chtv <= 4 * BN_THREADS_MAX ? 4 : 8;
+  pl.threads = cdiv(cdiv(chtv, pl.nj), 32) * 32;
+  pl.ok = true;
+  return pl;
+}
+// samples per stage: the largest of 4/2/1 whose two stages of `nst` slabs fit two CTAs per SM; 0 = none
+static int bnf_pick_u(size_t slab_bytes, int nst) {
+  for (int u = 4; u >= 1; u >>= 1)
+    if ((size_t)2 * nst * u * slab_bytes <= BN_SMEM_BUDGET) return u;
+  return 0;
+}
+
+#define DSTD_BNF_U(KERN, NJ_, u, grid, threads, smem, st, ...)                                        \
+  do {                                                                                                \
+    switch (u) {                                                                                      \
+      case 4:                                                                                         \
+        prefer_smem_carveout((const void*)KERN(NJ_, 4), true);                                        \
+        KERN(NJ_, 4)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                       \
+        break;                                                                                        \
+      case 2:                                                                                         \
+        prefer_smem_carveout((const void*)KERN(NJ_, 2), true);                                        \
+        KERN(NJ_, 2)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                       \
+        break;                                                                                        \
+      default:                                                                                        \
+        prefer_smem_carveout((const void*)KERN(NJ_, 1), true);                                        \
+        KERN(NJ_, 1)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                       \
+        break;                                                                                        \
+    }                                                                                                 \
+  } while (0)
+#define DSTD_BNF(KERN, nj, u, grid, threads, smem, st, ...)                                           \
+  do {                                                                                                \
+    if ((nj) == 4) DSTD_BNF_U(KERN, 4, u, grid, threads, smem, st, __VA_ARGS__);                      \
+    else DSTD_BNF_U(KERN, 8, u, grid, threads, smem, st, __VA_ARGS__);                                \
+  } while (0)
+
 // U (samples per pipeline stage) is a launch-time choice among the compiled instantiations
 #define DSTD_BN_CASE(kern, NJ_, u, grid, threads, smem, st, q)                       \
   do {                                                                                \
@@ -942,6 +1395,22 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
     count_launch();
     DSTD_LAUNCH_CHECK("bn_eval_stats");
   }
+  const BnFastPlan fp = bnf_plan(q.C, q.T, q.V, q.mask, {&q.y, &q.r, &q.out});
+  const int fu = fp.ok ? bnf_pick_u((size_t)fp.ch * tvb, nst) : 0;
+  if (fu) {   // bulk-copy staged kernel (see "fast path")
+    const dim3 grid(q.C / fp.ch, q.S);
+    const size_t smem = (size_t)2 * nst * fu * fp.ch * tvb;
+    int* err = device_error_word();
+#define DSTD_K_APPLY_R(NJ_, U_) bnf_apply_kernel<NJ_, U_, true>
+#define DSTD_K_APPLY(NJ_, U_) bnf_apply_kernel<NJ_, U_, false>
+    if (q.r.p) DSTD_BNF(DSTD_K_APPLY_R, fp.nj, fu, grid, fp.threads, smem, st, q, fp.ch, err);
+    else DSTD_BNF(DSTD_K_APPLY, fp.nj, fu, grid, fp.threads, smem, st, q, fp.ch, err);
+#undef DSTD_K_APPLY_R
+#undef DSTD_K_APPLY
+    count_launch();
+    DSTD_LAUNCH_CHECK("bnf_apply");
+    return DSTD_OK;
+  }
   DSTD_BN_DISPATCH_U(bn_apply_kernel, g.nj, u, dim3(q.C, q.S), g.threads, smu, st, q);
   count_launch();
   DSTD_LAUNCH_CHECK("bn_apply");
@@ -975,6 +1444,41 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
   BnGeom g = bn_geom(q.T, q.V);
   const size_t tv = (size_t)q.T * q.V * sizeof(float);
   const int nst = (q.r.p && q.prelu) ? 3 : 2;          // staged tensors: gout, y (, r); two pipeline stages
+  {
+    const bool use_r = q.r.p && q.prelu, has_gr = q.gr.p != nullptr, add = q.gadd.p != nullptr;
+    const bool combo = use_r ? has_gr : (!has_gr && !add);     // the instantiations the model uses
+    const bool gr_same = !has_gr || bnf_tfast(q.gr) == bnf_tfast(q.gy);
+    const BnFastPlan fp = (combo && gr_same) ? bnf_plan(q.C, q.T, q.V, q.mask, {&q.y, &q.r, &q.gout, &q.gy, &q.gr, &q.gadd})
+                                             : BnFastPlan{false, 0, 0, 0};
+    const int u1 = fp.ok ? bnf_pick_u((size_t)fp.ch * tv, nst) : 0;
+    const int u2 = fp.ok ? bnf_pick_u((size_t)fp.ch * tv, nst + (add ? 1 : 0)) : 0;
+    if (u1 && u2) {
+      const dim3 grid(q.C / fp.ch, q.S);
+      int* err = device_error_word();
+#define DSTD_K_RED_R(NJ_, U_) bnf_bwd_reduce_kernel<NJ_, U_, true>
+#define DSTD_K_RED(NJ_, U_) bnf_bwd_reduce_kernel<NJ_, U_, false>
+      if (use_r) DSTD_BNF(DSTD_K_RED_R, fp.nj, u1, grid, fp.threads, (size_t)2 * nst * u1 * fp.ch * tv, st, q, fp.ch, err);
+      else DSTD_BNF(DSTD_K_RED, fp.nj, u1, grid, fp.threads, (size_t)2 * nst * u1 * fp.ch * tv, st, q, fp.ch, err);
+#undef DSTD_K_RED_R
+#undef DSTD_K_RED
+      count_launch();
+      DSTD_LAUNCH_CHECK("bnf_bwd_reduce");
+      const int np = (int)(grid.x * grid.y);
+      const size_t smem2 = (size_t)2 * (nst + (add ? 1 : 0)) * u2 * fp.ch * tv;
+#define DSTD_K_APP_RA(NJ_, U_) bnf_bwd_apply_kernel<NJ_, U_, true, true, true>
+#define DSTD_K_APP_R(NJ_, U_) bnf_bwd_apply_kernel<NJ_, U_, true, true, false>
+#define DSTD_K_APP(NJ_, U_) bnf_bwd_apply_kernel<NJ_, U_, false, false, false>
+      if (use_r && add) DSTD_BNF(DSTD_K_APP_RA, fp.nj, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
+      else if (use_r) DSTD_BNF(DSTD_K_APP_R, fp.nj, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
+      else DSTD_BNF(DSTD_K_APP, fp.nj, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
+#undef DSTD_K_APP_RA
+#undef DSTD_K_APP_R
+#undef DSTD_K_APP
+      count_launch();
+      DSTD_LAUNCH_CHECK("bnf_bwd_apply");
+      return DSTD_OK;
+    }
+  }
   const int ub = bn_pick_u(tv, 2 * nst + 1, bn_ub_cap(), BN_SMEM_BUDGET);
   size_t sm_red = (size_t)2 * nst * ub * tv;
   if (sm_red < 2 * tv) sm_red = 2 * tv;

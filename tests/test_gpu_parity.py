@@ -296,6 +296,63 @@ def test_bn_act_abi(case):
         assert torch.equal(res2[0], res[0]) and torch.equal(res2[2], res[2]) and torch.equal(res2[3], res[3])
 
 
+BN_FAST_CASES = [
+    # n, c, t, v, y_order, r_order, out_order, prelu, training
+    (37, 8, 35, 22, "t", "t", 2, True, True),     # H3.6M plane (770 floats: two channels per slab), block BN, ragged splits
+    (9, 8, 35, 22, "v", None, 1, True, True),     # layer BN
+    (6, 4, 40, 23, "t", "t", 2, True, True),      # 3DPW plane (920: one channel per slab)
+    (5, 8, 35, 25, "t", "t", 2, True, True),      # CMU plane (875: four channels per slab)
+    (5, 8, 35, 25, "v", None, 1, True, False),    # eval mode
+    (3, 4, 10, 22, "t", None, 0, False, True),    # no PReLU, output like the input
+]
+
+
+@pytest.mark.parametrize("case", BN_FAST_CASES, ids=[str(i) for i in range(len(BN_FAST_CASES))])
+def test_bn_fast_path_equals_generic(case, monkeypatch):
+    """The bulk-copy staged BN kernels (bn_act.cu "fast path") against the generic ones on the same inputs: same
+    arithmetic per element and same summation order, so everything but the PReLU-slope gradient is bit-identical."""
+    n, c, t, v, yo, ro, out_order, use_prelu, training = case
+    g = torch.Generator().manual_seed(n * 7 + c)
+    be = cuda_backend()
+    from dstd_gcn_b200.ops import _out_like
+    y = to_dev(_ordered(g, n, c, t, v, yo) * 2.0 + 3.0)
+    r = to_dev(_ordered(g, n, c, t, v, ro)) if ro else None
+    gamma, beta = to_dev(rnd((c * v,), g, 0.5) + 1.0), to_dev(rnd((c * v,), g, 0.5))
+    prelu = to_dev(torch.tensor([0.25], dtype=torch.float64)) if use_prelu else None
+    ol = _out_like(y, out_order)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DSTD_BN_FAST", flag)
+        rm, rv = torch.zeros(c * v, device=DEV), torch.ones(c * v, device=DEV)
+        nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+        out, mean, istd = be.bn_act_forward(y, r, gamma, beta, rm, rv, nbt if training else None, prelu, None, False,
+                                            training, 1e-5, 0.1, ol if out_order else None)
+        gout = torch.empty_like(out)
+        gout.copy_(to_dev(rnd(tuple(out.shape), torch.Generator().manual_seed(5))))
+        bw = be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, training, r is not None)
+        bw2 = None
+        if r is not None:
+            gadd = torch.empty_like(out)
+            gadd.copy_(to_dev(rnd(tuple(out.shape), torch.Generator().manual_seed(6))))
+            bw2 = be.bn_act_backward(y, r, gout, gamma, beta, prelu, None, mean, istd, False, training, True, gadd)
+        torch.cuda.synchronize()
+        assert be.lib.dstd_device_error(0) == 0
+        res[flag] = (out, mean, istd, rm, rv, bw, bw2)
+    a, b = res["0"], res["1"]
+    for i in range(5):
+        assert torch.equal(a[i], b[i]), i
+    for bwa, bwb in ((a[5], b[5]), (a[6], b[6])):
+        if bwa is None:
+            continue
+        for nm, ta, tb in zip(("gy", "gr", "ggamma", "gbeta"), bwa, bwb):
+            if ta is None:
+                assert tb is None
+                continue
+            assert ta.stride() == tb.stride() and torch.equal(ta, tb), nm
+        if bwa[4] is not None:
+            assert max_abs(bwa[4], bwb[4]) <= 1e-5 * max(1.0, float(bwa[4].abs().max()))
+
+
 def test_bn_act_large_mean_is_stable():
     """millimetre-scale activations (mean >> std): shifted sums keep the variance accurate."""
     be = cuda_backend()
