@@ -218,41 +218,96 @@ int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, float* gm2_part, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------ aggregation, forward
-//   xa[n,b,c,p,w] = sum_v x[n,c,p,v] xmu_b[p,v,w]  (c < Cin; row Cin: x := 1)       CTA = (p, n); warp = channel, lanes = w
+//   xa[n,b,c,p,w] = sum_v x[n,c,p,v] xmu_b[p,v,w]  (c < Cin; row Cin: x := 1)
+// CTA = (p, n); the K x K adjacency of (n, b, p) sits in shared memory (rows / columns beyond K are zero, so the inner
+// loops carry no guards); warp = 8 channels x 128 columns (4 per lane) register tile: per four v the warp reads
+// 8 broadcast float4 of x and 16 row segments of xmu for 128 FMAs per lane.
+constexpr int AG_CW = 8;                                      // channels per warp tile
+__host__ __device__ inline int ag_kp4(int K) { return (K + 3) & ~3; }
+__host__ __device__ inline int ag_kl(int K) { return ((K + 31) & ~31) + 1; }   // odd row stride >= 32-multiple + 1
+
+// xmu_b[v][w] = alpha pd[n,b,p][v][w] + (A .* W + R)[v][w] (transposed when adj_t) into xm[KP4][KL], zero padded
+__device__ __forceinline__ void ag_build_xm(const AggParams& q, int n, int b, int p, float alpha, float* xm, int KP4, int KL) {
+  const int K = q.K, KK = K * K;
+  for (int i = threadIdx.x; i < KP4 * KL; i += blockDim.x) xm[i] = 0.f;
+  __syncthreads();
+  const float* pdp = q.pd + ((long long)(n * q.nb + b) * q.P + p) * KK;
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) {
+    const int r = i / K, c = i - r * K;
+    float a = __ldg(q.adj[b] + i);
+    if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + i);
+    if (q.adj_r[b]) a += __ldg(q.adj_r[b] + i);
+    const float val = fmaf(alpha, __ldg(pdp + i), a);
+    if (q.adj_t) xm[c * KL + r] = val; else xm[r * KL + c] = val;
+  }
+}
+
+template <int NI>   // 32-column groups per lane: ceil(K / 32)
 __global__ void __launch_bounds__(256) aggregate_fwd_gen_kernel(AggParams q) {
   extern __shared__ __align__(16) float smem[];
-  const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, C1 = Cin + 1, KL = K + 1;
-  float* xm = smem;                  // [K][KL]   xmu[v][w]
-  float* xr = xm + K * KL;           // [8][K]    one input row per warp
+  const int K = q.K, P = q.P, Cin = q.Cin, C1 = Cin + 1, KP4 = ag_kp4(K), KL = ag_kl(K);
+  float* xm = smem;                          // [KP4][KL]   xmu[v][w]
+  float* xs = xm + ((KP4 * KL + 3) & ~3);    // [8 warps][AG_CW][KP4]   input rows of the warp's channels
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = blockIdx.x, n = blockIdx.y;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
+  float* xw = xs + warp * AG_CW * KP4;
+  const float* xb = q.x.p + vix(q.x, n, 0, p, 0);
   for (int b = 0; b < q.nb; ++b) {
+    __syncthreads();                         // every warp is done with the previous branch's xm
+    ag_build_xm(q, n, b, p, alpha, xm, KP4, KL);
     __syncthreads();
-    const float* pdp = q.pd + ((long long)(n * q.nb + b) * P + p) * KK;
-    for (int i = tid; i < KK; i += 256) {
-      const int r = i / K, c = i - r * K;
-      float a = __ldg(q.adj[b] + i);
-      if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + i);
-      if (q.adj_r[b]) a += __ldg(q.adj_r[b] + i);
-      const float val = fmaf(alpha, __ldg(pdp + i), a);
-      if (q.adj_t) xm[c * KL + r] = val; else xm[r * KL + c] = val;
-    }
-    __syncthreads();
-    for (int c = warp; c < C1; c += 8) {
-      for (int v = lane; v < K; v += 32) xr[warp * K + v] = c < Cin ? __ldg(q.x.p + vix(q.x, n, c, p, v)) : 1.0f;
-      __syncwarp();
-      float acc[GEN_MAX / 32] = {0.f, 0.f, 0.f, 0.f};
-      for (int v = 0; v < K; ++v) {
-        const float xv = xr[warp * K + v];
+    for (int c0 = warp * AG_CW; c0 < C1; c0 += 8 * AG_CW) {
+      // the warp's AG_CW rows: all loads of a lane issued before the first store (one exposed latency per tile)
+      float stg[AG_CW][NI];
 #pragma unroll
-        for (int i = 0; i < GEN_MAX / 32; ++i)
-          if (lane + 32 * i < K) acc[i] = fmaf(xv, xm[v * KL + lane + 32 * i], acc[i]);
+      for (int cl = 0; cl < AG_CW; ++cl) {
+        const int c = c0 + cl;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int v = lane + 32 * i;
+          stg[cl][i] = v < K ? (c < Cin ? __ldg(xb + (long long)c * q.x.sc + (long long)v * q.x.sk) : (c == Cin ? 1.0f : 0.f)) : 0.f;
+        }
       }
-      float* dst = q.xa + (((long long)(n * q.nb + b) * C1 + c) * P + p) * K;
 #pragma unroll
-      for (int i = 0; i < GEN_MAX / 32; ++i)
-        if (lane + 32 * i < K) dst[lane + 32 * i] = acc[i];
+      for (int cl = 0; cl < AG_CW; ++cl)
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          if (lane + 32 * i < KP4) xw[cl * KP4 + lane + 32 * i] = stg[cl][i];
+      __syncwarp();
+      float acc[AG_CW][NI];
+#pragma unroll
+      for (int cl = 0; cl < AG_CW; ++cl)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) acc[cl][i] = 0.f;
+      for (int v4 = 0; v4 < KP4; v4 += 4) {
+        float4 xv[AG_CW];
+#pragma unroll
+        for (int cl = 0; cl < AG_CW; ++cl) xv[cl] = *reinterpret_cast<const float4*>(xw + cl * KP4 + v4);
+#pragma unroll
+        for (int vv = 0; vv < 4; ++vv) {
+          const float* row = xm + (v4 + vv) * KL + lane;
+          float m[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) m[i] = row[32 * i];      // KL - 1 >= 32 NI: in bounds, zero beyond K
+#pragma unroll
+          for (int cl = 0; cl < AG_CW; ++cl) {
+            const float xe = vv == 0 ? xv[cl].x : vv == 1 ? xv[cl].y : vv == 2 ? xv[cl].z : xv[cl].w;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[cl][i] = fmaf(xe, m[i], acc[cl][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int cl = 0; cl < AG_CW; ++cl) {
+        const int c = c0 + cl;
+        if (c < C1) {
+          float* dst = q.xa + (((long long)(n * q.nb + b) * C1 + c) * P + p) * K;
+#pragma unroll
+          for (int i = 0; i < NI; ++i)
+            if (lane + 32 * i < K) dst[lane + 32 * i] = acc[cl][i];
+        }
+      }
       __syncwarp();
     }
   }
@@ -260,95 +315,209 @@ __global__ void __launch_bounds__(256) aggregate_fwd_gen_kernel(AggParams q) {
 
 int launch_aggregate_fwd_gen(const AggParams& q, cudaStream_t st) {
   DSTD_REQUIRE(generic_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED, "aggregate_fwd_gen: P=%d K=%d outside limits", q.P, q.K);
-  const size_t smem = ((size_t)q.K * (q.K + 1) + 8 * q.K) * sizeof(float);
-  ensure_max_smem((const void*)aggregate_fwd_gen_kernel);
+  const int KP4 = ag_kp4(q.K), KL = ag_kl(q.K);
+  const size_t smem = ((size_t)((KP4 * KL + 3) & ~3) + (size_t)8 * AG_CW * KP4) * sizeof(float);
   dim3 grid(q.P, q.N);
-  aggregate_fwd_gen_kernel<<<grid, 256, smem, st>>>(q);
+#define DSTD_AGF(NI_)                                                     \
+  {                                                                       \
+    ensure_max_smem((const void*)aggregate_fwd_gen_kernel<NI_>);          \
+    aggregate_fwd_gen_kernel<NI_><<<grid, 256, smem, st>>>(q);            \
+  }
+  switch ((q.K + 31) / 32) {
+    case 1: DSTD_AGF(1) break;
+    case 2: DSTD_AGF(2) break;
+    case 3: DSTD_AGF(3) break;
+    default: DSTD_AGF(4) break;
+  }
+#undef DSTD_AGF
   count_launch();
   return check_launch("aggregate_fwd_gen");
 }
 
 // ------------------------------------------------------------------------------------------ aggregation, backward
 //   gx[n,c,p,v]      = sum_b sum_w gxa_b[c,p,w] xmu_b[p,v,w]
-//   gxmu_b[p,v,w]    = sum_{c <= Cin} xaug[c,p,v] gxa_b[c,p,w]          (accumulated in shared memory over channel chunks)
-// CTA = (p, n).  gx accumulates over the branches in a shared tile of the CTA's channels chunk by chunk.
-constexpr int AB_CC = 32;      // channels per chunk
-
-__global__ void __launch_bounds__(256) aggregate_bwd_gen_kernel(AggParams q) {
+//   gxmu_b[p,v,w]    = sum_{c <= Cin} xaug[c,p,v] gxa_b[c,p,w]
+// CTA = (p, n), channels in chunks of CC (a multiple of 32, ~16 KB per staged tensor) through shared memory, every global
+// load of a chunk issued before the first store.  gx: warp = 4 channels x 32 NI rows v, the odd row stride of xmu makes
+// the lane = v reads conflict free.  gxmu: 4 x 4 (v, w) register tiles kept for the whole channel loop (two float4
+// reads per 16 FMAs).  K > 44: up to four tiles per thread, all channels.  Small K (at most 128 tiles): G = 256 / tiles
+// thread groups split the channels of a chunk and their tiles are summed in group order at the end (deterministic).
+// gx accumulates over the branches in global memory (same thread, same address).
+template <int NI, bool SMALL>
+__global__ void __launch_bounds__(256) aggregate_bwd_gen_kernel(AggParams q, int CC, int G) {
   extern __shared__ __align__(16) float smem[];
-  const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, C1 = Cin + 1, KL = K + 1;
-  float* xm = smem;                       // [K][KL]     xmu_b[v][w]
-  float* gxm = xm + K * KL;               // [K][KL]     gxmu_b[v][w]
-  float* xs = gxm + K * KL;               // [AB_CC][K]  x rows (ones row included)
-  float* gs = xs + AB_CC * K;             // [AB_CC][K]  gxa_b rows
+  const int K = q.K, P = q.P, KK = K * K, Cin = q.Cin, C1 = Cin + 1, KP4 = ag_kp4(K), KL = ag_kl(K);
+  float* xm = smem;                          // [KP4][KL]   xmu_b[v][w]
+  float* xs = xm + ((KP4 * KL + 3) & ~3);    // [CC][KP4]  x rows (ones row included), zero padded
+  float* gs = xs + CC * KP4;                 // [CC][KP4]  gxa_b rows, zero padded
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = blockIdx.x, n = blockIdx.y;
   const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
+  const int TW = KP4 >> 2, ntile = TW * TW;  // 4 x 4 tiles of the (v, w) grid
+  constexpr int NT = SMALL ? 1 : 4;          // tiles per thread: SMALL (tid % ntile, channel group tid / ntile), else tid + 256 j
+  const int grp = SMALL ? tid / ntile : 0, tsm = SMALL ? tid - grp * ntile : 0;
+  const bool act_sm = SMALL && grp < G;
+  const float* xb = q.x.p + vix(q.x, n, 0, p, 0);
+  const int chunk_e = CC * KP4;
   for (int b = 0; b < q.nb; ++b) {
     __syncthreads();
-    const float* pdp = q.pd + ((long long)(n * q.nb + b) * P + p) * KK;
-    for (int i = tid; i < KK; i += 256) {
-      const int r = i / K, c = i - r * K;
-      float a = __ldg(q.adj[b] + i);
-      if (q.adj_w[b]) a *= __ldg(q.adj_w[b] + i);
-      if (q.adj_r[b]) a += __ldg(q.adj_r[b] + i);
-      const float val = fmaf(alpha, __ldg(pdp + i), a);
-      if (q.adj_t) xm[c * KL + r] = val; else xm[r * KL + c] = val;
-    }
-    for (int i = tid; i < K * KL; i += 256) gxm[i] = 0.f;
-    for (int c0 = 0; c0 < C1; c0 += AB_CC) {
+    ag_build_xm(q, n, b, p, alpha, xm, KP4, KL);
+    float tacc[NT][16];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) tacc[j][e] = 0.f;
+    const float* gb = q.gxa + ((long long)(n * q.nb + b) * C1 * P + p) * K;
+    for (int c0 = 0; c0 < C1; c0 += CC) {
       __syncthreads();
-      for (int i = tid; i < AB_CC * K; i += 256) {
-        const int cl = i / K, k = i - cl * K, c = c0 + cl;
-        xs[i] = c < Cin ? __ldg(q.x.p + vix(q.x, n, c, p, k)) : (c == Cin ? 1.0f : 0.f);
-        gs[i] = c < C1 ? __ldg(q.gxa + (((long long)(n * q.nb + b) * C1 + c) * P + p) * K + k) : 0.f;
+      for (int base = 0; base < chunk_e; base += 256 * 8) {
+        float xa_[8], ga_[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + tid + 256 * u;
+          const int cl = i / KP4, k = i - cl * KP4, c = c0 + cl;
+          const bool in = i < chunk_e && k < K;
+          xa_[u] = in ? (c < Cin ? __ldg(xb + (long long)c * q.x.sc + (long long)k * q.x.sk) : (c == Cin ? 1.0f : 0.f)) : 0.f;
+          ga_[u] = (in && c < C1) ? __ldg(gb + (long long)c * P * K + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + tid + 256 * u;
+          if (i < chunk_e) {
+            xs[i] = xa_[u];
+            gs[i] = ga_[u];
+          }
+        }
       }
       __syncthreads();
-      // gx rows of this chunk: warp = channel, lanes = v
-      for (int cl = warp; cl < AB_CC; cl += 8) {
-        const int c = c0 + cl;
-        if (c < Cin) {
-          float acc[GEN_MAX / 32] = {0.f, 0.f, 0.f, 0.f};
-          for (int w = 0; w < K; ++w) {
-            const float gv = gs[cl * K + w];
+      // gx rows of this chunk: warp = CC/8 channels in groups of 4, lane = rows v = lane + 32 i
+      for (int cg = 0; cg < CC / 8; cg += 4) {
+        const int clb = warp * (CC / 8) + cg;
+        if (c0 + clb >= Cin) break;
+        float acc[4][NI];
 #pragma unroll
-            for (int i = 0; i < GEN_MAX / 32; ++i)
-              if (lane + 32 * i < K) acc[i] = fmaf(gv, xm[(lane + 32 * i) * KL + w], acc[i]);
-          }
+        for (int cl = 0; cl < 4; ++cl)
 #pragma unroll
-          for (int i = 0; i < GEN_MAX / 32; ++i) {
+          for (int i = 0; i < NI; ++i) acc[cl][i] = 0.f;
+        for (int w4 = 0; w4 < KP4; w4 += 4) {
+          float4 gv[4];
+#pragma unroll
+          for (int cl = 0; cl < 4; ++cl) gv[cl] = *reinterpret_cast<const float4*>(gs + (clb + cl) * KP4 + w4);
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
             const int v = lane + 32 * i;
-            if (v < K) {
-              float* d = q.gx.p + vix(q.gx, n, c, p, v);
-              *d = (b > 0 ? *d : 0.f) + acc[i];
+            if (v < KP4) {                      // rows K .. KP4-1 of xm are zero
+              const float* row = xm + v * KL + w4;
+              const float m0 = row[0], m1 = row[1], m2 = row[2], m3 = row[3];
+#pragma unroll
+              for (int cl = 0; cl < 4; ++cl)
+                acc[cl][i] = fmaf(gv[cl].x, m0, fmaf(gv[cl].y, m1, fmaf(gv[cl].z, m2, fmaf(gv[cl].w, m3, acc[cl][i]))));
+            }
+          }
+        }
+#pragma unroll
+        for (int cl = 0; cl < 4; ++cl) {
+          const int c = c0 + clb + cl;
+          if (c < Cin) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const int v = lane + 32 * i;
+              if (v < K) {
+                float* d = q.gx.p + vix(q.gx, n, c, p, v);
+                *d = (b > 0 ? *d : 0.f) + acc[cl][i];
+              }
             }
           }
         }
       }
-      // gxmu += xs^T gs over the chunk: thread = (v, w) pairs
-      for (int e = tid; e < KK; e += 256) {
-        const int v = e / K, w = e - v * K;
-        float s = 0.f;
-#pragma unroll 8
-        for (int cl = 0; cl < AB_CC; ++cl) s = fmaf(xs[cl * K + v], gs[cl * K + w], s);
-        gxm[v * KL + w] += s;
+      // gxmu tiles += xs^T gs over the chunk
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int t = SMALL ? tsm : tid + 256 * j;
+        if (SMALL ? act_sm : t < ntile) {
+          const int tv = t / TW, tw = t - tv * TW;
+          const float* xr = xs + 4 * tv;
+          const float* gr = gs + 4 * tw;
+          const int cstep = SMALL ? G : 1;
+#pragma unroll 4
+          for (int cl = SMALL ? grp : 0; cl < CC; cl += cstep) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + cl * KP4);
+            const float4 g = *reinterpret_cast<const float4*>(gr + cl * KP4);
+            tacc[j][0] = fmaf(a.x, g.x, tacc[j][0]); tacc[j][1] = fmaf(a.x, g.y, tacc[j][1]);
+            tacc[j][2] = fmaf(a.x, g.z, tacc[j][2]); tacc[j][3] = fmaf(a.x, g.w, tacc[j][3]);
+            tacc[j][4] = fmaf(a.y, g.x, tacc[j][4]); tacc[j][5] = fmaf(a.y, g.y, tacc[j][5]);
+            tacc[j][6] = fmaf(a.y, g.z, tacc[j][6]); tacc[j][7] = fmaf(a.y, g.w, tacc[j][7]);
+            tacc[j][8] = fmaf(a.z, g.x, tacc[j][8]); tacc[j][9] = fmaf(a.z, g.y, tacc[j][9]);
+            tacc[j][10] = fmaf(a.z, g.z, tacc[j][10]); tacc[j][11] = fmaf(a.z, g.w, tacc[j][11]);
+            tacc[j][12] = fmaf(a.w, g.x, tacc[j][12]); tacc[j][13] = fmaf(a.w, g.y, tacc[j][13]);
+            tacc[j][14] = fmaf(a.w, g.z, tacc[j][14]); tacc[j][15] = fmaf(a.w, g.w, tacc[j][15]);
+          }
+        }
       }
     }
-    __syncthreads();
     float* dst = q.gxm + ((long long)(n * q.nb + b) * P + p) * KK;
-    for (int i = tid; i < KK; i += 256) {
-      const int r = i / K, c = i - r * K;
-      dst[i] = q.adj_t ? gxm[c * KL + r] : gxm[r * KL + c];
+    if (SMALL) {
+      // group partials through the (now free) chunk buffers, summed in group order
+      __syncthreads();
+      float* scr = xs;                         // [G][KP4][KP4]  (host checks that it fits in the two chunk buffers)
+      if (act_sm) {
+        const int tv = tsm / TW, tw = tsm - tv * TW;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) scr[(grp * KP4 + 4 * tv + (e >> 2)) * KP4 + 4 * tw + (e & 3)] = tacc[0][e];
+      }
+      __syncthreads();
+      for (int i = tid; i < KK; i += 256) {
+        const int v = i / K, w = i - v * K;
+        float sres = 0.f;
+        for (int g = 0; g < G; ++g) sres += scr[(g * KP4 + v) * KP4 + w];
+        dst[q.adj_t ? (w * K + v) : i] = sres;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int t = tid + 256 * j;
+        if (t < ntile) {
+          const int tv = t / TW, tw = t - tv * TW;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int v = 4 * tv + (e >> 2), w = 4 * tw + (e & 3);
+            if (v < K && w < K) dst[q.adj_t ? (w * K + v) : (v * K + w)] = tacc[j][e];
+          }
+        }
+      }
     }
   }
 }
 
 int launch_aggregate_bwd_gen(const AggParams& q, cudaStream_t st) {
   DSTD_REQUIRE(generic_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED, "aggregate_bwd_gen: P=%d K=%d outside limits", q.P, q.K);
-  const size_t smem = ((size_t)2 * q.K * (q.K + 1) + 2 * AB_CC * q.K) * sizeof(float);
-  ensure_max_smem((const void*)aggregate_bwd_gen_kernel);
+  const int KP4 = ag_kp4(q.K), KL = ag_kl(q.K), ntile = (KP4 / 4) * (KP4 / 4);
+  int CC = 4096 / KP4 / 32 * 32;
+  const int c1r = (q.Cin + 1 + 31) / 32 * 32;
+  if (CC > c1r) CC = c1r;
+  if (CC > 256) CC = 256;
+  if (CC < 32) CC = 32;
+  const bool small = ntile <= 128;
+  int G = small ? 256 / ntile : 1;
+  while (small && G > 1 && (size_t)G * KP4 * KP4 > (size_t)2 * CC * KP4) --G;   // partials must fit in the chunk buffers
+  const size_t smem = ((size_t)((KP4 * KL + 3) & ~3) + (size_t)2 * CC * KP4) * sizeof(float);
   dim3 grid(q.P, q.N);
-  aggregate_bwd_gen_kernel<<<grid, 256, smem, st>>>(q);
+#define DSTD_AGB(NI_, SM_)                                                      \
+  {                                                                             \
+    ensure_max_smem((const void*)aggregate_bwd_gen_kernel<NI_, SM_>);           \
+    aggregate_bwd_gen_kernel<NI_, SM_><<<grid, 256, smem, st>>>(q, CC, G);      \
+  }
+  const int ni = (q.K + 31) / 32;
+  if (small) {
+    if (ni == 1) DSTD_AGB(1, true) else DSTD_AGB(2, true)       // ntile <= 128 means K <= 44
+  } else {
+    switch (ni) {
+      case 2: DSTD_AGB(2, false) break;
+      case 3: DSTD_AGB(3, false) break;
+      default: DSTD_AGB(4, false) break;
+    }
+  }
+#undef DSTD_AGB
   count_launch();
   return check_launch("aggregate_bwd_gen");
 }
