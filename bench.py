@@ -409,13 +409,15 @@ def run_infer(args, model, be, dev, rank, world, t, v, t_in):
         model.eval()
         static_in = host[0].to(dev)
         resident = [h.to(dev) for h in host]
+        from dstd_gcn_b200.engine import forward_overlapped
+        fwd = (lambda z: forward_overlapped(model, z, args.infer_streams)) if args.infer_streams > 1 else model
         for _ in range(2):
-            out = model(static_in)
+            out = fwd(static_in)
         torch.cuda.synchronize()
         l0 = be.launches
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            static_out = model(static_in)
+            static_out = fwd(static_in)
         launches_per_step = be.launches - l0
     out_host = torch.empty_like(static_out, device="cpu").pin_memory()
 
@@ -473,7 +475,8 @@ def run_infer(args, model, be, dev, rank, world, t, v, t_in):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": host[0].numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps, "cuda_graph": True, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps, "cuda_graph": True, "infer_streams": args.infer_streams,
+            "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "scope": f"forward only: {bytes_fwd} algorithmic B per sample (SURVEY.md 8d)"},
             "gpu_eager_baseline": eager,
@@ -547,6 +550,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default 256; 32 for stress)")
     ap.add_argument("--workload", default="h36m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--infer-streams", type=int, default=4,
+                    help="--mode infer: independent sub-batches of the eval forward on this many streams (1 = one chain)")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train: the headline metric; infer: eval-mode forward sweep (BASELINE.json config 4)")
     ap.add_argument("--variant", default="dstdgcn", choices=["dstdgcn", "dstdgcn_fast"])

@@ -252,6 +252,40 @@ def predict(model, inputs):
     return model(inputs.view(n, t, vc // 3, 3)).reshape(n, -1, vc)
 
 
+_EVAL_STREAMS = {}
+
+
+@torch.no_grad()
+def forward_overlapped(model, x, parts=2):
+    """Eval-mode forward of ``x [N, T, V, 3]`` as ``parts`` independent sub-batches on separate streams.
+
+    In eval mode (BatchNorm on running statistics, engine/prediction.py:340-353) the samples of a batch do not
+    interact, so the sub-batches are independent kernel chains: the persistent one-CTA-per-SM kernels of one chain
+    fill their tails and set-up phases with CTAs of the other, exactly as the two passes of the training step do.
+    Result identical to ``model(x)`` (same kernels per sample).  Capturable in a CUDA graph (fork / join by events)."""
+    assert not model.training, "forward_overlapped is an eval-mode path (BatchNorm batch statistics couple the samples)"
+    n = x.shape[0]
+    parts = max(1, min(parts, n))
+    if parts == 1 or not x.is_cuda:
+        return model(x)
+    main = torch.cuda.current_stream()
+    key = (x.device.index, parts)
+    if key not in _EVAL_STREAMS:
+        _EVAL_STREAMS[key] = [torch.cuda.Stream(device=x.device) for _ in range(parts - 1)]
+    bounds = [n * i // parts for i in range(parts + 1)]
+    outs = [None] * parts
+    for i, st in enumerate(_EVAL_STREAMS[key]):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            outs[i + 1] = model(x[bounds[i + 1]:bounds[i + 2]])
+    outs[0] = model(x[bounds[0]:bounds[1]])
+    for st in _EVAL_STREAMS[key]:
+        main.wait_stream(st)
+    for o in outs[1:]:
+        o.record_stream(main)
+    return torch.cat(outs, dim=0)
+
+
 @torch.no_grad()
 def evaluate(model, batches, input_n, eval_frame, dim_used=None, joint_to_ignore=None, joint_equal=None):
     """Per-frame MPJPE of ``PredictionEngine.test`` (engine/prediction.py:319-430) on the sm_100a forward.

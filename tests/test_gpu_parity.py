@@ -814,6 +814,33 @@ def test_two_stream_passes_match_sequential(monkeypatch):
             assert torch.equal(b, res[1][1][k]), k
 
 
+def test_forward_overlapped_equals_plain_forward():
+    """`engine.forward_overlapped`: the eval forward as two / three independent sub-batches on side streams gives the
+    same result as one chain (same kernels per sample), eagerly and inside a CUDA graph."""
+    from dstd_gcn_b200.engine import forward_overlapped
+    import bench
+    torch.manual_seed(9)
+    m = _perturbed(_mod("fast").DSTDGCN(6, 10, 25, 0.0, 22, 16, 2, "h36m")).to(DEV)
+    with torch.no_grad():
+        m.train()
+        m(bench.synthetic_batch(8, 35, 22, 10, seed=1)[0].view(8, 35, 22, 3).to(DEV))   # running stats off (0, 1)
+        m.eval()
+        x = bench.synthetic_batch(11, 35, 22, 10, seed=2)[0].view(11, 35, 22, 3).to(DEV)
+        ref = m(x)
+        for parts in (2, 3):
+            assert torch.equal(forward_overlapped(m, x, parts), ref)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = forward_overlapped(m, x, 2)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    m.train()
+    with pytest.raises(AssertionError):
+        forward_overlapped(m, x, 2)
+
+
 def test_prefetcher_feeds_the_device_path():
     """`data.DevicePrefetcher`: pinned double-buffered H2D on a side stream + device-side window gathers give the same
     tuples as the host construction, in order, and train a step."""
