@@ -132,7 +132,7 @@ struct GcWs {
 static size_t gc_fwd_ws(int Cin, int Cout, int nb, int P = 40, int K = 40) {
   return arena_need({(size_t)Cout * nb * (Cin + 1) * 4, (size_t)4 * nb * (Cin + 1) * 4,
                      (size_t)nb * (Cin + 1) * ((Cout + 7) / 8 * 8) * 4, aggmix_tc_ws_floats(Cin, Cout, P, K, nb) * 4,
-                     unit_tc_ws_bytes(nb)});
+                     unit_tc_ws_bytes(nb), bgemm_tc_ws_bytes(Cout, nb * (Cin + 1))});
 }
 // shapes beyond the specialised tiles (P or K > 40) run the shape-generic kernels of generic.cu
 static bool use_generic(int Cin, int P, int K) { return !(dynadj_supported(P, K) && aggregate_supported(Cin, P, K)); }
@@ -149,7 +149,7 @@ static size_t gc_bwd_ws(int N, int Cin, int Cout, int P, int K, int nb) {
   return arena_need({(size_t)Cout * nb * C1 * 4, (size_t)4 * nb * C1 * 4, unf * G * nb * C1 * 4, G * nb * K * 4,
                      G * nb * 4 * 4, unf * S1 * Cout * nb * C1 * 4, ((size_t)S1 > ps ? (size_t)S1 : ps) * 4 * nb * C1 * 4,
                      (size_t)S2 * nb * P * (2 * P + 1) * 4, (size_t)S2 * nb * K * K * 4, (size_t)S2 * nb * 4,
-                     ps * nb * Cout * Cin * 4, ps * nb * Cout * 4, unit_tc_ws_bytes(nb),
+                     ps * nb * Cout * Cin * 4, ps * nb * Cout * 4, unit_tc_ws_bytes(nb), bgemm_tc_ws_bytes(nb * (int)C1, Cout),
                      use_generic(Cin, P, K) ? dynadj_bwd_gen_ws_floats(N, nb, P, K) * 4 : 0});
 }
 
@@ -249,6 +249,7 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   float* wcatT = ar.take<float>((size_t)nb * C1 * ((Cout + 7) / 8 * 8));
   float* wtc = ar.take<float>(aggmix_tc_ws_floats(Cin, Cout, P, K, nb));
   void* wunit = ar.take<char>(unit_tc_ws_bytes(nb));
+  void* wbt = ar.take<char>(bgemm_tc_ws_bytes(Cout, nb * C1));               // weight images of the tcgen05 channel GEMM
   const bool use_unit = !a->xa && unit_tc_supported(Cin, Cout, P, K, nb);    // every contraction on tcgen05 (unit_tc.cu)
   const bool use_tc = !a->xa && aggmix_tc_supported(Cin, Cout, P, K, nb);   // tcgen05 channel mix only (aggmix_tc.cu)
   const bool fused = !use_generic(Cin, P, K) && (use_unit || aggmix_supported(Cin, Cout, P, K, nb));
@@ -309,6 +310,7 @@ extern "C" int dstd_gc_forward(const dstd_gc_fwd_args* a, dstd_stream_t stream) 
   g2.in = dense_view(a->xa, nb * C1, P, K); g2.ones_row = -1;
   g2.out = mk(a->out);
   g2.add = mk(a->skip);
+  g2.tc_ws = bgemm_tc_ws_bytes(Cout, nb * C1) ? wbt : nullptr;
   return launch_bgemm(g2, st);
 }
 
@@ -345,6 +347,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   float* p_wf = ar.take<float>(ps * nb * Cout * Cin);
   float* p_bf = ar.take<float>(ps * nb * Cout);
   void* wunit = ar.take<char>(unit_tc_ws_bytes(nb));
+  void* wbt = ar.take<char>(bgemm_tc_ws_bytes(nb * C1, Cout));
   float* gm2_part = ar.take<float>(generic ? dynadj_bwd_gen_ws_floats(N, nb, P, K) : 0);
 
   PackParams pk;
@@ -383,6 +386,7 @@ extern "C" int dstd_gc_backward(const dstd_gc_bwd_args* a, dstd_stream_t stream)
   g1.in = mk(a->gout); g1.ones_row = -1;
   g1.out = dense_view(gxa, nb * C1, P, K);
   g1.add = View4{nullptr, 0, 0, 0, 0};
+  g1.tc_ws = bgemm_tc_ws_bytes(nb * C1, Cout) ? wbt : nullptr;
   if ((rc = launch_bgemm(g1, st))) return rc;
 
   // 2. g(wcat)[o, j] = sum gout[o] xa[j]

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) bgemm_kernel(BgemmParam
 
 int launch_bgemm(BgemmParams q, cudaStream_t st) {
   if (q.G <= 0 || q.M <= 0) return 0;
+  if (q.tc_ws && bgemm_tc_supported(q.M, q.Kd)) return launch_bgemm_tc(q, q.tc_ws, st);   // tcgen05 path (bgemm_tc.cu)
   // full 64-row tiles on the wide kernel, a remainder of <= 16 rows on the skinny one
   int full = (q.M / 64) * 64;
   int rem = q.M - full;

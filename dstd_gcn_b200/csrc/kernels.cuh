@@ -19,8 +19,12 @@ struct BgemmParams {
   View4 out;
   View4 add;           // optional (p == null)
   int m0, m1;          // filled by the launcher
+  void* tc_ws = nullptr;   // optional: bgemm_tc_ws_bytes(M, Kd) of workspace enables the tcgen05 kernel (bgemm_tc.cu)
 };
 int launch_bgemm(BgemmParams q, cudaStream_t st);
+bool bgemm_tc_supported(int M, int Kd);
+size_t bgemm_tc_ws_bytes(int M, int Kd);
+int launch_bgemm_tc(const BgemmParams& q, void* ws, cudaStream_t st);
 
 struct WgradParams {
   int M, Cd;

@@ -171,6 +171,10 @@ STRESS_CASES = [
     (2, 24, 24, 22, 125, 1, "kp", False, True),     # temporal unit: K = 125 frames, layer skip, transposed view
     (1, 72, 80, 125, 22, 2, "pk", False, False),    # wide channels, spatial
     (1, 16, 3, 22, 125, 1, "pk", True, False),      # output-like block, adjacency used transposed
+    # channel GEMMs on tcgen05 (bgemm_tc.cu: M >= 128 output rows, >= 64 reduction rows)
+    (2, 130, 136, 35, 22, 2, "pk", False, True),    # ragged M tiles / K chunks (fwd 136 x 262, bwd 262 x 136), layer skip
+    (1, 256, 256, 125, 22, 2, "pk", False, False),  # stress spatial unit: bwd has five M tiles (514 rows, 64-position tiles)
+    (1, 256, 256, 22, 125, 1, "kp", False, True),   # stress temporal unit
 ]
 
 
