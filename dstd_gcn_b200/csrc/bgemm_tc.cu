@@ -33,8 +33,8 @@ struct BgemmTcGeom {
 static __host__ __device__ inline BgemmTcGeom tc_geom(int M, int Kd) {
   BgemmTcGeom g;
   g.mtiles = (M + 127) / 128;
-  g.np = g.mtiles <= 4 ? 128 : 64;
-  g.kc = g.mtiles <= 2 ? 32 : 16;
+  g.np = g.mtiles <= 4 ? 128 : 96;     // TMEM: mtiles * np <= 512 columns
+  g.kc = 16;   // two CTAs per SM for up to two M tiles (86 KB, 256 TMEM columns each): their phases interleave
   g.nchunk = (Kd + g.kc - 1) / g.kc;
   int cols = g.mtiles * g.np, pw = 32;
   while (pw < cols) pw <<= 1;
@@ -81,10 +81,10 @@ __global__ void bgemm_tc_pack_kernel(const float* __restrict__ w, long long wsc,
 constexpr int BT_NT = 256;
 
 template <int NP, int KC>
-__global__ void __launch_bounds__(BT_NT, 1) bgemm_tc_kernel(BgemmParams q, BgemmTcGeom g, const unsigned char* __restrict__ wimg,
+__global__ void __launch_bounds__(BT_NT, 2) bgemm_tc_kernel(BgemmParams q, BgemmTcGeom g, const unsigned char* __restrict__ wimg,
                                                             int* err) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int PAIRS = NP / 2, RSTEP = BT_NT / PAIRS, PP = KC / RSTEP;   // rows r0 + RSTEP j, j < PP, per thread
+  constexpr int PAIRS = NP / 2, RSTEP = BT_NT / PAIRS, PP = (KC + RSTEP - 1) / RSTEP;   // rows r0 + RSTEP j (< KC), j < PP, per thread
   unsigned char* abuf = smem;                                   // [2][a_chunk]
   unsigned char* bbuf = abuf + 2 * g.a_chunk;                   // [2][b_chunk]
   long long* col_in = reinterpret_cast<long long*>(bbuf + 2 * g.b_chunk);
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(BT_NT, 1) bgemm_tc_kernel(BgemmParams q, Bgemm
 
   // this thread's position pair and first row of the B chunk
   const int pi = tid % PAIRS, r0 = tid / PAIRS;
-  const long long off0 = col_in[2 * pi], off1 = col_in[2 * pi + 1];
+  const bool conv = r0 < RSTEP;                    // NP = 96: 240 of the 256 threads convert
+  const long long off0 = conv ? col_in[2 * pi] : -1, off1 = conv ? col_in[2 * pi + 1] : -1;
   const bool vec = off0 >= 0 && off1 == off0 + 1 && !((off0 | q.in.sc) & 1) && !(reinterpret_cast<uintptr_t>(q.in.p) & 7);
   float pv[PP][2];
   auto load_chunk = [&](int c) {
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(BT_NT, 1) bgemm_tc_kernel(BgemmParams q, Bgemm
     for (int j = 0; j < PP; ++j) {
       const int kd = c * KC + r0 + RSTEP * j;
       pv[j][0] = pv[j][1] = 0.f;
-      if (kd < q.Kd) {
+      if (kd < q.Kd && r0 + RSTEP * j < KC) {
         if (kd == q.ones_row) {
           pv[j][0] = off0 >= 0 ? 1.f : 0.f;
           pv[j][1] = off1 >= 0 ? 1.f : 0.f;
@@ -148,6 +149,14 @@ __global__ void __launch_bounds__(BT_NT, 1) bgemm_tc_kernel(BgemmParams q, Bgemm
     }
   };
   load_chunk(0);
+  auto issue_w = [&](int c) {     // thread 0: one bulk copy brings the weight images of chunk c
+    umma::mbar_expect_tx(&bar[c & 1], g.a_chunk);
+    umma::bulk_g2s(abuf + (size_t)(c & 1) * g.a_chunk, wimg + (size_t)c * g.a_chunk, g.a_chunk, &bar[c & 1]);
+  };
+  if (tid == 0) {
+    issue_w(0);
+    if (g.nchunk > 1) issue_w(1);
+  }
 
   const uint32_t abase = umma::smem_u32(abuf), bbase = umma::smem_u32(bbuf);
   const uint32_t idesc = umma::idesc_bf16(128, NP, 0, 1);
@@ -156,14 +165,11 @@ __global__ void __launch_bounds__(BT_NT, 1) bgemm_tc_kernel(BgemmParams q, Bgemm
   for (int c = 0; c < NC; ++c) {
     const int buf = c & 1, use = c >> 1;
     if (c >= 2) ok &= umma::mbar_wait(&bar[2 + buf], (uint32_t)(use - 1) & 1u);   // the MMAs of chunk c - 2 retired
-    if (tid == 0) {
-      umma::mbar_expect_tx(&bar[buf], g.a_chunk);
-      umma::bulk_g2s(abuf + (size_t)buf * g.a_chunk, wimg + (size_t)c * g.a_chunk, g.a_chunk, &bar[buf]);
-    }
     unsigned char* bdst = bbuf + (size_t)buf * g.b_chunk;
 #pragma unroll
     for (int j = 0; j < PP; ++j) {
       const int r = r0 + RSTEP * j;
+      if (!conv || r >= KC) continue;
       uint32_t h0, m0, l0, h1, m1, l1;
       umma::split_bf16x3(pv[j][0], h0, m0, l0);
       umma::split_bf16x3(pv[j][1], h1, m1, l1);
@@ -200,6 +206,12 @@ __global__ void __launch_bounds__(BT_NT, 1) bgemm_tc_kernel(BgemmParams q, Bgemm
         }
       }
       umma::commit_elect(&bar[2 + buf]);
+      // weights of chunk c + 1 (c >= 1; chunks 0 and 1 were requested up front): their buffer is free once the MMAs of
+      // chunk c - 1, issued one iteration ago, have retired; the copy then lands under the tensor work of chunk c
+      if (c >= 1 && c + 1 < NC) {
+        ok &= umma::mbar_wait(&bar[2 + (buf ^ 1)], (uint32_t)((c - 1) >> 1) & 1u);
+        if (lane == 0) issue_w(c + 1);
+      }
     }
   }
   // every MMA retired: the last commit covers all earlier ones
@@ -276,9 +288,8 @@ int launch_bgemm_tc(const BgemmParams& q, void* ws, cudaStream_t st) {
     ensure_max_smem((const void*)bgemm_tc_kernel<NP_, KC_>);                             \
     bgemm_tc_kernel<NP_, KC_><<<tiles, BT_NT, g.smem, st>>>(q, g, img, err);             \
   }
-  if (g.np == 128 && g.kc == 32) DSTD_BT(128, 32)
-  else if (g.np == 128) DSTD_BT(128, 16)
-  else DSTD_BT(64, 16)
+  if (g.np == 128) DSTD_BT(128, 16)
+  else DSTD_BT(96, 16)
 #undef DSTD_BT
   count_launch();
   return check_launch("bgemm_tc");
