@@ -15,51 +15,79 @@ bool generic_supported(int P, int K) { return P >= 1 && K >= 1 && P <= GEN_MAX &
 
 // ------------------------------------------------------------------------------------------ dynamic adjacency, forward
 //   pd[n,b,p,e] = brm[p] + sum_{k'=(r,p')} Wrm[p][k'] tanh(m[n,b,r,p',v] - m[n,b,2+r,p',w]),  e = v*K + w
-// CTA = (64-pair tile, b, n); thread = pair e, rows p = pg, pg + 4, ...  (pg = tid / 64)
-constexpr int DG_TP = 64, DG_KC = 32;
+// CTA = (128-pair tile, b, n).  Per chunk of 16 reduction rows k' the m rows are staged in shared memory, the pairwise tanh
+// tile D[k'][e] is produced once (one pair per thread and row: the (v, w) decode is per-thread constant), and the
+// contraction runs on register tiles: thread = 4 consecutive pairs x RP rows p, per k' one float4 of D and RP/4 float4 of
+// Wrm for 4 RP FMAs.
+constexpr int DG_TP = 128, DG_KC = 16;
 
+template <int RP>    // rows per thread: 8 row groups x RP >= P
 __global__ void __launch_bounds__(256) dynadj_fwd_gen_kernel(DynAdjFwdParams q) {
-  __shared__ float Ds[DG_KC][DG_TP];
-  __shared__ float Ws[DG_KC][GEN_MAX];
+  __shared__ __align__(16) float Ds[DG_KC][DG_TP];
+  __shared__ __align__(16) float Ws[DG_KC][8 * RP];
+  __shared__ float m1c[DG_KC][GEN_MAX], m2c[DG_KC][GEN_MAX];
   const int P = q.P, K = q.K, KK = K * K, P2 = 2 * P;
-  const int tid = threadIdx.x, el = tid & 63, pg = tid >> 6;
+  const int tid = threadIdx.x, eg = tid & 31, rg = tid >> 5;      // pairs 4 eg .. 4 eg + 3, rows rg RP .. rg RP + RP - 1
   const int b = blockIdx.y, n = blockIdx.z, e0 = blockIdx.x * DG_TP;
   const float* mb = q.m + (long long)(n * q.nb + b) * 4 * P * K;
   const float* wrm = q.w_rm[b];
-  float acc[GEN_MAX / 4];
+  // the pair this thread produces in the D tile (rows tid / 128 + 2 j of the chunk)
+  const int de = tid & (DG_TP - 1), dk0 = tid >> 7;
+  const int e_d = e0 + de, dv = e_d < KK ? e_d / K : 0, dw = e_d < KK ? e_d - dv * K : 0;
+  float acc[RP][4];
 #pragma unroll
-  for (int j = 0; j < GEN_MAX / 4; ++j) acc[j] = 0.f;
+  for (int j = 0; j < RP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
   for (int k0 = 0; k0 < P2; k0 += DG_KC) {
-    for (int i = tid; i < DG_KC * DG_TP; i += 256) {
-      const int kk = i / DG_TP, ee = i - kk * DG_TP, kp = k0 + kk, e = e0 + ee;
-      float d = 0.f;
-      if (kp < P2 && e < KK) {
-        const int r = kp / P, pp = kp - r * P, v = e / K, w = e - v * K;
-        d = fast_tanh(__ldg(mb + (r * P + pp) * K + v) - __ldg(mb + ((2 + r) * P + pp) * K + w));
+    __syncthreads();          // the previous chunk's tiles are consumed
+    for (int i = tid; i < DG_KC * K; i += 256) {
+      const int kk = i / K, x = i - kk * K, kp = k0 + kk;
+      float a = 0.f, c = 0.f;
+      if (kp < P2) {
+        const int r = kp / P, pp = kp - r * P;
+        a = __ldg(mb + (r * P + pp) * K + x);
+        c = __ldg(mb + ((2 + r) * P + pp) * K + x);
       }
-      Ds[kk][ee] = d;
+      m1c[kk][x] = a;
+      m2c[kk][x] = c;
     }
-    for (int i = tid; i < DG_KC * P; i += 256) {
-      const int p = i / DG_KC, kk = i - p * DG_KC;
-      Ws[kk][p] = (k0 + kk < P2) ? __ldg(wrm + (long long)p * P2 + k0 + kk) : 0.f;
+    for (int i = tid; i < DG_KC * 8 * RP; i += 256) {
+      const int kk = i / (8 * RP), p = i - kk * (8 * RP);
+      Ws[kk][p] = (k0 + kk < P2 && p < P) ? __ldg(wrm + (long long)p * P2 + k0 + kk) : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
-    for (int kk = 0; kk < DG_KC; ++kk) {
-      const float d = Ds[kk][el];
-#pragma unroll
-      for (int j = 0; j < GEN_MAX / 4; ++j)
-        if (pg + 4 * j < P) acc[j] = fmaf(Ws[kk][pg + 4 * j], d, acc[j]);
+    for (int j = 0; j < DG_KC / 2; ++j) {
+      const int kk = dk0 + 2 * j;
+      Ds[kk][de] = (k0 + kk < P2 && e_d < KK) ? fast_tanh(m1c[kk][dv] - m2c[kk][dw]) : 0.f;
     }
     __syncthreads();
-  }
-  const int e = e0 + el;
-  if (e < KK) {
-    float* dst = q.pd + (long long)(n * q.nb + b) * P * KK + e;
+#pragma unroll 2
+    for (int kk = 0; kk < DG_KC; ++kk) {
+      const float4 d = *reinterpret_cast<const float4*>(&Ds[kk][4 * eg]);
 #pragma unroll
-    for (int j = 0; j < GEN_MAX / 4; ++j) {
-      const int p = pg + 4 * j;
-      if (p < P) dst[(long long)p * KK] = acc[j] + __ldg(q.b_rm[b] + p);
+      for (int j4 = 0; j4 < RP; j4 += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][rg * RP + j4]);
+#define DSTD_DG_ROW(U, WV)                                 \
+  acc[j4 + U][0] = fmaf(WV, d.x, acc[j4 + U][0]);          \
+  acc[j4 + U][1] = fmaf(WV, d.y, acc[j4 + U][1]);          \
+  acc[j4 + U][2] = fmaf(WV, d.z, acc[j4 + U][2]);          \
+  acc[j4 + U][3] = fmaf(WV, d.w, acc[j4 + U][3]);
+        DSTD_DG_ROW(0, w.x) DSTD_DG_ROW(1, w.y) DSTD_DG_ROW(2, w.z) DSTD_DG_ROW(3, w.w)
+#undef DSTD_DG_ROW
+      }
+    }
+  }
+  float* dst = q.pd + (long long)(n * q.nb + b) * P * KK;
+#pragma unroll
+  for (int j = 0; j < RP; ++j) {
+    const int p = rg * RP + j;
+    if (p < P) {
+      const float bv = __ldg(q.b_rm[b] + p);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + 4 * eg + u;
+        if (e < KK) dst[(long long)p * KK + e] = acc[j][u] + bv;
+      }
     }
   }
 }
@@ -67,7 +95,9 @@ __global__ void __launch_bounds__(256) dynadj_fwd_gen_kernel(DynAdjFwdParams q) 
 int launch_dynadj_fwd_gen(const DynAdjFwdParams& q, cudaStream_t st) {
   DSTD_REQUIRE(generic_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED, "dynadj_fwd_gen: P=%d K=%d outside limits (<= %d)", q.P, q.K, GEN_MAX);
   dim3 grid(cdiv(q.K * q.K, DG_TP), q.nb, q.N);
-  dynadj_fwd_gen_kernel<<<grid, 256, 0, st>>>(q);
+  if (q.P <= 32) dynadj_fwd_gen_kernel<4><<<grid, 256, 0, st>>>(q);
+  else if (q.P <= 64) dynadj_fwd_gen_kernel<8><<<grid, 256, 0, st>>>(q);
+  else dynadj_fwd_gen_kernel<16><<<grid, 256, 0, st>>>(q);
   count_launch();
   return check_launch("dynadj_fwd_gen");
 }
@@ -80,22 +110,27 @@ int launch_dynadj_fwd_gen(const DynAdjFwdParams& q, cudaStream_t st) {
 //   gWrm[p][k'] = sum_e gP[p][e] D[k'][e]   gbrm[p] = sum_e gP[p][e]         -> partial slot (n, tile) (already x alpha)
 //   gA_eff[e]   = sum_p gxm[p][e]                                            -> slot n (the tiles own disjoint e ranges)
 //   galpha      = sum gxm pd                                                 -> partial slot (n, tile)
-constexpr int DB_KC = 16, DB_TP = 128;
+constexpr int DB_KC = 16, DB_TP = 128, DB_GLD = DB_TP + 4;   // GLD % 4 == 0: float4 reads along the pairs
 
 int dynadj_gen_tiles(int K) {
   const int VT = DB_TP / K > 0 ? DB_TP / K : 1;
   return (K + VT - 1) / VT;
 }
 
+// Register-tiled: the two contractions of a chunk of 16 reduction rows k' run on 4 x 2 (pairs x rows, step c) and
+// 2 x 4 (output rows x reduction rows, step d) thread tiles with float4 shared-memory reads; Wrm and the m rows of the
+// chunk are staged in shared memory (the first version read Wrm from global memory inside the FMA loop).
 __global__ void __launch_bounds__(256) dynadj_bwd_gen_kernel(DynAdjBwdParams q, float* __restrict__ gm2_part, int NT) {
   extern __shared__ __align__(16) float smem[];
   const int P = q.P, K = q.K, KK = K * K, P2 = 2 * P, P21 = P2 + 1;
   const int VT = max(1, DB_TP / K);                       // K <= 128: at least one row per tile
-  constexpr int GLD = DB_TP + 1;
-  float* gPs = smem;                         // [P][GLD]
-  float* Ds = gPs + P * GLD;                 // [DB_KC][DB_TP]
+  float* gPs = smem;                         // [P][DB_GLD]   alpha * gxm, columns >= tp zero
+  float* Wc = gPs + P * DB_GLD;              // [P][DB_KC]    Wrm[p][k0 + kk]
+  float* Ds = Wc + ((P * DB_KC + 3) & ~3);   // [DB_KC][DB_TP]
   float* Gs = Ds + DB_KC * DB_TP;            // [DB_KC][DB_TP]
-  float* red = Gs + DB_KC * DB_TP;           // [32]
+  float* m1c = Gs + DB_KC * DB_TP;           // [DB_KC][DB_TP]  m1 rows at v0 .. v0 + vt - 1
+  float* m2c = m1c + DB_KC * DB_TP;          // [DB_KC][DB_TP]  m2 rows, all w
+  float* red = m2c + DB_KC * DB_TP;          // [32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, n = blockIdx.y, tile = blockIdx.z;
   const int v0 = tile * VT, vt = min(VT, K - v0), tp = vt * K, e0 = v0 * K;
@@ -111,12 +146,16 @@ __global__ void __launch_bounds__(256) dynadj_bwd_gen_kernel(DynAdjBwdParams q, 
   float* g2 = gm2_part + (((long long)(n * q.nb + b)) * NT + tile) * P2 * K;
   float ga = 0.f;
 
-  // a. gP tile, alpha gradient
-  for (int i = tid; i < P * tp; i += 256) {
-    const int p = i / tp, e = i - p * tp;
-    const float g = __ldg(gx + (long long)p * KK + e0 + e);
-    ga = fmaf(g, __ldg(pdb + (long long)p * KK + e0 + e), ga);
-    gPs[p * GLD + e] = alpha * g;
+  // a. gP tile (zero beyond tp), alpha gradient
+  for (int i = tid; i < P * DB_TP; i += 256) {
+    const int p = i / DB_TP, e = i - p * DB_TP;
+    float v = 0.f;
+    if (e < tp) {
+      const float g = __ldg(gx + (long long)p * KK + e0 + e);
+      ga = fmaf(g, __ldg(pdb + (long long)p * KK + e0 + e), ga);
+      v = alpha * g;
+    }
+    gPs[p * DB_GLD + e] = v;
   }
   __syncthreads();
   for (int e = tid; e < tp; e += 256) {          // static-adjacency gradient: the raw sum (alpha may be 0)
@@ -126,49 +165,93 @@ __global__ void __launch_bounds__(256) dynadj_bwd_gen_kernel(DynAdjBwdParams q, 
   }
   for (int p = warp; p < P; p += 8) {            // conv_rm bias gradient: row sums (fixed order: lanes then butterfly)
     float s = 0.f;
-    for (int e = lane; e < tp; e += 32) s += gPs[p * GLD + e];
+    for (int e = lane; e < tp; e += 32) s += gPs[p * DB_GLD + e];
     s = warp_sum(s);
     if (lane == 0) pw[(long long)p * P21 + P2] = s;
   }
+  // thread-constant decodes
+  const int de = tid & (DB_TP - 1), dk0 = tid >> 7;                    // D tile: pair de, rows dk0 + 2 j
+  const int dvl = de < tp ? de / K : 0, dw = de < tp ? de - dvl * K : 0;
+  const int ceg = tid & 31, ckg = tid >> 5;                            // step c: pairs 4 ceg .., rows 2 ckg, 2 ckg + 1
+  const int dkq = tid & 3, dpg = tid >> 2;                             // step d: rows 4 dkq .., outputs p = 2 dpg, 2 dpg + 1
   for (int k0 = 0; k0 < P2; k0 += DB_KC) {
-    // b. D chunk
-    for (int i = tid; i < DB_KC * tp; i += 256) {
-      const int kk = i / tp, e = i - kk * tp, kp = k0 + kk;
-      float d = 0.f;
+    // stage the m rows and the Wrm columns of this chunk
+    for (int i = tid; i < DB_KC * DB_TP; i += 256) {
+      const int kk = i >> 7, x = i & (DB_TP - 1), kp = k0 + kk;
+      float a = 0.f, c = 0.f;
       if (kp < P2) {
-        const int r = kp / P, pp = kp - r * P, vl = e / K, w = e - vl * K;
-        d = fast_tanh(__ldg(mb + (r * P + pp) * K + v0 + vl) - __ldg(mb + ((2 + r) * P + pp) * K + w));
+        const int r = kp / P, pp = kp - r * P;
+        if (x < vt) a = __ldg(mb + (r * P + pp) * K + v0 + x);
+        if (x < K) c = __ldg(mb + ((2 + r) * P + pp) * K + x);
       }
-      Ds[kk * DB_TP + e] = d;
+      m1c[i] = a;
+      m2c[i] = c;
+    }
+    for (int i = tid; i < P * DB_KC; i += 256) {
+      const int p = i / DB_KC, kk = i - p * DB_KC;
+      Wc[i] = (k0 + kk < P2) ? __ldg(wrm + (long long)p * P2 + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+    // b. D chunk
+#pragma unroll
+    for (int j = 0; j < DB_KC / 2; ++j) {
+      const int kk = dk0 + 2 * j;
+      Ds[kk * DB_TP + de] = (k0 + kk < P2 && de < tp) ? fast_tanh(m1c[kk * DB_TP + dvl] - m2c[kk * DB_TP + dw]) : 0.f;
     }
     __syncthreads();
     // c. gS = (Wrm^T gP) (1 - D^2)
-    for (int i = tid; i < DB_KC * tp; i += 256) {
-      const int kk = i / tp, e = i - kk * tp, kp = k0 + kk;
-      float s = 0.f;
-      if (kp < P2) {
-        for (int p = 0; p < P; ++p) s = fmaf(__ldg(wrm + (long long)p * P2 + kp), gPs[p * GLD + e], s);
-        const float d = Ds[kk * DB_TP + e];
-        s *= 1.f - d * d;
+    {
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* gp = gPs + 4 * ceg;
+      const float* wc = Wc + 2 * ckg;
+#pragma unroll 4
+      for (int p = 0; p < P; ++p) {
+        const float4 g = *reinterpret_cast<const float4*>(gp + p * DB_GLD);
+        const float2 w = *reinterpret_cast<const float2*>(wc + p * DB_KC);
+        a0[0] = fmaf(w.x, g.x, a0[0]); a0[1] = fmaf(w.x, g.y, a0[1]); a0[2] = fmaf(w.x, g.z, a0[2]); a0[3] = fmaf(w.x, g.w, a0[3]);
+        a1[0] = fmaf(w.y, g.x, a1[0]); a1[1] = fmaf(w.y, g.y, a1[1]); a1[2] = fmaf(w.y, g.z, a1[2]); a1[3] = fmaf(w.y, g.w, a1[3]);
       }
-      Gs[kk * DB_TP + e] = s;
+      const float4 d0 = *reinterpret_cast<const float4*>(Ds + (2 * ckg) * DB_TP + 4 * ceg);
+      const float4 d1 = *reinterpret_cast<const float4*>(Ds + (2 * ckg + 1) * DB_TP + 4 * ceg);
+      *reinterpret_cast<float4*>(Gs + (2 * ckg) * DB_TP + 4 * ceg) =
+          make_float4(a0[0] * (1.f - d0.x * d0.x), a0[1] * (1.f - d0.y * d0.y), a0[2] * (1.f - d0.z * d0.z), a0[3] * (1.f - d0.w * d0.w));
+      *reinterpret_cast<float4*>(Gs + (2 * ckg + 1) * DB_TP + 4 * ceg) =
+          make_float4(a1[0] * (1.f - d1.x * d1.x), a1[1] * (1.f - d1.y * d1.y), a1[2] * (1.f - d1.z * d1.z), a1[3] * (1.f - d1.w * d1.w));
     }
-    // d. gWrm[p][k'] = sum_e gP[p][e] D[k'][e]   (lanes = p: the GLD = 129 pitch keeps the row reads conflict free)
-    for (int i = tid; i < DB_KC * P; i += 256) {
-      const int kk = i / P, p = i - kk * P, kp = k0 + kk;
-      if (kp < P2) {
-        float s = 0.f;
-        for (int e = 0; e < tp; ++e) s = fmaf(gPs[p * GLD + e], Ds[kk * DB_TP + e], s);
-        pw[(long long)p * P21 + kp] = s;
+    // d. gWrm[p][k'] = sum_e gP[p][e] D[k'][e]
+    if (2 * dpg < P) {
+      float a[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const float* g0 = gPs + (2 * dpg) * DB_GLD;
+      const float* g1 = gPs + (2 * dpg + 1 < P ? 2 * dpg + 1 : 2 * dpg) * DB_GLD;
+      const float* dr = Ds + (4 * dkq) * DB_TP;
+      const int tp4 = (tp + 3) & ~3;
+      for (int e4 = 0; e4 < tp4; e4 += 4) {
+        const float4 x0 = *reinterpret_cast<const float4*>(g0 + e4);
+        const float4 x1 = *reinterpret_cast<const float4*>(g1 + e4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 d = *reinterpret_cast<const float4*>(dr + u * DB_TP + e4);
+          a[0][u] = fmaf(x0.x, d.x, fmaf(x0.y, d.y, fmaf(x0.z, d.z, fmaf(x0.w, d.w, a[0][u]))));
+          a[1][u] = fmaf(x1.x, d.x, fmaf(x1.y, d.y, fmaf(x1.z, d.z, fmaf(x1.w, d.w, a[1][u]))));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kp = k0 + 4 * dkq + u;
+        if (kp < P2) {
+          pw[(long long)(2 * dpg) * P21 + kp] = a[0][u];
+          if (2 * dpg + 1 < P) pw[(long long)(2 * dpg + 1) * P21 + kp] = a[1][u];
+        }
       }
     }
     __syncthreads();
-    // e. row / column sums of gS
-    for (int i = tid; i < DB_KC * vt; i += 256) {
-      const int kk = i / vt, vl = i - kk * vt, kp = k0 + kk;
-      if (kp < P2) {
-        float s = 0.f;
-        for (int w = 0; w < K; ++w) s += Gs[kk * DB_TP + vl * K + w];
+    // e. row sums (warp per (k', v): lanes over w, fixed butterfly) and column sums of gS
+    for (int o = warp; o < DB_KC * vt; o += 8) {
+      const int kk = o / vt, vl = o - kk * vt, kp = k0 + kk;
+      float s = 0.f;
+      for (int w = lane; w < K; w += 32) s += Gs[kk * DB_TP + vl * K + w];
+      s = warp_sum(s);
+      if (lane == 0 && kp < P2) {
         const int r = kp / P, pp = kp - r * P;
         gmb[(r * P + pp) * K + v0 + vl] = s;
       }
@@ -205,7 +288,7 @@ int launch_dynadj_bwd_gen(const DynAdjBwdParams& q, float* gm2_part, cudaStream_
   DSTD_REQUIRE(generic_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED, "dynadj_bwd_gen: P=%d K=%d outside limits (<= %d)", q.P, q.K, GEN_MAX);
   const int NT = dynadj_gen_tiles(q.K);
   DSTD_REQUIRE(q.S == q.N * NT && gm2_part, DSTD_ERR_BAD_ARG, "dynadj_bwd_gen: one partial slot per (sample, tile) expected");
-  const size_t smem = ((size_t)q.P * (DB_TP + 1) + 2 * DB_KC * DB_TP + 32) * sizeof(float);
+  const size_t smem = ((size_t)q.P * DB_GLD + ((q.P * DB_KC + 3) & ~3) + 4 * DB_KC * DB_TP + 32) * sizeof(float);
   ensure_max_smem((const void*)dynadj_bwd_gen_kernel);
   dim3 grid(q.nb, q.N, NT);
   dynadj_bwd_gen_kernel<<<grid, 256, smem, st>>>(q, gm2_part, NT);
