@@ -258,6 +258,218 @@ __global__ void __launch_bounds__(BT_NT, 2) bgemm_tc_kernel(BgemmParams q, Bgemm
   if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)g.tmem_cols);
 }
 
+// ================================================================================= weight gradient on tcgen05
+//   G[i][c] = sum_g A[i][g] B[c][g]      (A = gout [M rows], B = xa [Cd rows], g = the N*P*K positions: split-K)
+// Both operands are position-contiguous, i.e. K-major row images [rows][32 positions] for the tensor core.  CTA = (split
+// of the positions, 128-row tile of A, column block of B of NBW <= 256 rows): per chunk of 32 positions all threads load
+// position pairs (coalesced), split them three ways and store the images; warp 0 issues 2 k-steps x 6 products into ONE
+// TMEM accumulator [128 x NBW]; tcgen05.commit -> mbarrier releases the (single) stage, the loads of the next chunk are
+// already in registers; two CTAs per SM interleave their convert / MMA phases.  Epilogue: tcgen05.ld -> the split's
+// partial [M][Cd] (summed by reduce_segments in a fixed order, like the CUDA-core wgrad).
+constexpr int WT_KC = 32;
+
+struct WgradTcGeom {
+  int mtiles, nblocks, nbw, tmem_cols, S;
+  long long cols_per_split;
+  uint32_t sbo, a_plane, b_plane;
+  size_t smem;
+};
+static WgradTcGeom wgrad_tc_geom(int M, int Cd, long long G, int S_max) {
+  WgradTcGeom g;
+  g.mtiles = (M + 127) / 128;
+  g.nblocks = (Cd + 255) / 256;
+  g.nbw = ((Cd + g.nblocks - 1) / g.nblocks + 15) / 16 * 16;
+  int pw = 32;
+  while (pw < g.nbw) pw <<= 1;
+  g.tmem_cols = pw;
+  int S = (2 * num_sms() + g.mtiles * g.nblocks - 1) / (g.mtiles * g.nblocks);
+  if (S > S_max) S = S_max;
+  if (S < 1) S = 1;
+  long long per = (G + S - 1) / S;
+  g.cols_per_split = (per + WT_KC - 1) / WT_KC * WT_KC;
+  g.S = (int)((G + g.cols_per_split - 1) / g.cols_per_split);
+  g.sbo = (uint32_t)umma::img16_sbo_b(WT_KC);
+  g.a_plane = 16u * g.sbo;
+  g.b_plane = (uint32_t)(g.nbw / 8) * g.sbo;
+  g.smem = (size_t)3 * (g.a_plane + g.b_plane) + 64;
+  return g;
+}
+
+__global__ void __launch_bounds__(BT_NT, 2) wgrad_tc_kernel(WgradParams q, WgradTcGeom g, int* err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* aimg = smem;                         // [3 planes][128 rows][32 positions]
+  unsigned char* bimg = aimg + 3 * g.a_plane;         // [3 planes][nbw rows][32 positions]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(bimg + 3 * g.b_plane);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mt = blockIdx.y / g.nblocks, nbk = blockIdx.y - mt * g.nblocks;
+  const int i0 = mt * 128, c0 = nbk * g.nbw, NBJ = g.nbw / 16;
+  const int PK = q.P * q.K;
+  const long long gbeg = (long long)blockIdx.x * g.cols_per_split;
+  long long gend = gbeg + g.cols_per_split;
+  if (gend > q.G) gend = q.G;
+
+  if (tid == 0) {
+    umma::mbar_init(&bar[0], 1);
+    umma::mbar_init_fence();
+  }
+  if (warp == 0) umma::tmem_alloc(tslot, (uint32_t)g.tmem_cols);
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tslot), 0);
+
+  const int pi = tid & 15, rl = tid >> 4;            // position pair of the chunk, rows rl + 16 j
+  float pa[8][2], pb[16][2];
+  auto pos_off = [&](const View4& w, long long gg) -> long long {
+    if (gg >= gend) return -1;
+    const int n = (int)(gg / PK);
+    const int j = (int)(gg - (long long)n * PK);
+    const int p = j / q.K, k = j - p * q.K;
+    return vix(w, n, 0, p, k);
+  };
+  auto load_chunk = [&](long long gc) {
+    const long long gg = gc + 2 * pi;
+    const long long a0 = pos_off(q.a, gg), a1 = pos_off(q.a, gg + 1), b0 = pos_off(q.b, gg), b1 = pos_off(q.b, gg + 1);
+    const bool va = a0 >= 0 && a1 == a0 + 1 && !((a0 | q.a.sc) & 1) && !(reinterpret_cast<uintptr_t>(q.a.p) & 7);
+    const bool vb = b0 >= 0 && b1 == b0 + 1 && !((b0 | q.b.sc) & 1) && !(reinterpret_cast<uintptr_t>(q.b.p) & 7);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + rl + 16 * j;
+      pa[j][0] = pa[j][1] = 0.f;
+      if (i < q.M) {
+        if (va) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(q.a.p + a0 + (long long)i * q.a.sc));
+          pa[j][0] = t.x;
+          pa[j][1] = t.y;
+        } else {
+          if (a0 >= 0) pa[j][0] = __ldg(q.a.p + a0 + (long long)i * q.a.sc);
+          if (a1 >= 0) pa[j][1] = __ldg(q.a.p + a1 + (long long)i * q.a.sc);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int cc = c0 + rl + 16 * j;
+      pb[j][0] = pb[j][1] = 0.f;
+      if (j < NBJ && cc < q.Cd) {
+        if (cc == q.b_ones_row) {
+          pb[j][0] = b0 >= 0 ? 1.f : 0.f;
+          pb[j][1] = b1 >= 0 ? 1.f : 0.f;
+        } else if (vb) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(q.b.p + b0 + (long long)cc * q.b.sc));
+          pb[j][0] = t.x;
+          pb[j][1] = t.y;
+        } else {
+          if (b0 >= 0) pb[j][0] = __ldg(q.b.p + b0 + (long long)cc * q.b.sc);
+          if (b1 >= 0) pb[j][1] = __ldg(q.b.p + b1 + (long long)cc * q.b.sc);
+        }
+      }
+    }
+  };
+  if (gbeg < gend) load_chunk(gbeg);
+
+  const uint32_t abase = umma::smem_u32(aimg), bbase = umma::smem_u32(bimg);
+  const uint32_t idesc = umma::idesc_bf16(128, g.nbw, 0, 0);
+  const uint32_t hi = dhi(g.sbo);
+  bool ok = true;
+  int it = 0;
+  for (long long gc = gbeg; gc < gend; gc += WT_KC, ++it) {
+    if (it > 0) ok &= umma::mbar_wait(&bar[0], (uint32_t)(it - 1) & 1u);     // the MMAs of the previous chunk read the images
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t h0, m0, l0, h1, m1, l1;
+      umma::split_bf16x3(pa[j][0], h0, m0, l0);
+      umma::split_bf16x3(pa[j][1], h1, m1, l1);
+      unsigned char* d = aimg + umma::img16_off_b(rl + 16 * j, 2 * pi, (int)g.sbo);
+      *reinterpret_cast<uint32_t*>(d) = umma::pack_bf16(h0, h1);
+      *reinterpret_cast<uint32_t*>(d + g.a_plane) = umma::pack_bf16(m0, m1);
+      *reinterpret_cast<uint32_t*>(d + 2 * g.a_plane) = umma::pack_bf16(l0, l1);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < NBJ) {
+        uint32_t h0, m0, l0, h1, m1, l1;
+        umma::split_bf16x3(pb[j][0], h0, m0, l0);
+        umma::split_bf16x3(pb[j][1], h1, m1, l1);
+        unsigned char* d = bimg + umma::img16_off_b(rl + 16 * j, 2 * pi, (int)g.sbo);
+        *reinterpret_cast<uint32_t*>(d) = umma::pack_bf16(h0, h1);
+        *reinterpret_cast<uint32_t*>(d + g.b_plane) = umma::pack_bf16(m0, m1);
+        *reinterpret_cast<uint32_t*>(d + 2 * g.b_plane) = umma::pack_bf16(l0, l1);
+      }
+    }
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    if (gc + WT_KC < gend) load_chunk(gc + WT_KC);
+    if (warp == 0) {
+      umma::fence_after();
+      const uint32_t leader = elect_lane();
+#pragma unroll
+      for (int s = 0; s < WT_KC / 16; ++s) {
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          const uint32_t pla = (t == 0) ? 2u : (t == 2 || t == 3) ? 1u : 0u;
+          const uint32_t plb = (t == 1) ? 2u : (t == 2 || t == 4) ? 1u : 0u;
+          const uint32_t as = abase + pla * g.a_plane + (uint32_t)s * 2u * umma::IMG16_LBO_B;
+          const uint32_t bs = bbase + plb * g.b_plane + (uint32_t)s * 2u * umma::IMG16_LBO_B;
+          umma::mma_f16_lohi(tmem, dlo(as, umma::IMG16_LBO_B), hi, dlo(bs, umma::IMG16_LBO_B), hi, idesc,
+                             (it == 0 && s == 0 && t == 0) ? 0u : 1u, leader);
+        }
+      }
+      umma::commit_elect(&bar[0]);
+    }
+  }
+  if (it > 0) {
+    ok &= umma::mbar_wait(&bar[0], (uint32_t)(it - 1) & 1u);
+    umma::fence_after();
+  }
+  if (!ok && tid == 0 && err) *(volatile int*)err = 4;
+
+  // epilogue: lane = row of the tile, columns in two halves -> this split's partial
+  {
+    const int lq = warp & 3, chalf = warp >> 2, half = g.nbw / 2, i = i0 + lq * 32 + lane;
+    float* dst = q.partial + ((long long)blockIdx.x * q.M + i) * q.Cd + c0;
+    for (int c8 = 0; c8 < half; c8 += 8) {
+      uint32_t v[8];
+      const int col = chalf * half + c8;
+      if (it > 0) {
+        umma::tmem_ld8(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col, v);
+        umma::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = 0u;
+      }
+      if (i < q.M) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + col + u < q.Cd) dst[col + u] = __uint_as_float(v[u]);
+      }
+    }
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)g.tmem_cols);
+}
+
+bool wgrad_tc_supported(int M, int Cd) {
+  const char* e = getenv("DSTD_BGEMM_TC");
+  if (e && atoi(e) == 0) return false;
+  return M >= 128 && Cd >= 128;
+}
+
+// partial must hold wgrad_splits(G) * M * Cd floats (the split count used here never exceeds it); fills q.S
+int launch_wgrad_tc(WgradParams& q, cudaStream_t st) {
+  const WgradTcGeom g = wgrad_tc_geom(q.M, q.Cd, q.G, wgrad_splits(q.G));
+  q.S = g.S;
+  q.cols_per_split = g.cols_per_split;
+  int* err = device_error_word();
+  ensure_max_smem((const void*)wgrad_tc_kernel);
+  wgrad_tc_kernel<<<dim3(g.S, g.mtiles * g.nblocks), BT_NT, g.smem, st>>>(q, g, err);
+  count_launch();
+  return check_launch("wgrad_tc");
+}
+
 bool bgemm_tc_supported(int M, int Kd) {
   const char* e = getenv("DSTD_BGEMM_TC");            // read per call: the tests compare both paths
   if (e && atoi(e) == 0) return false;

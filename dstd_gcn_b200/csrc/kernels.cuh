@@ -39,6 +39,8 @@ struct WgradParams {
 };
 int wgrad_splits(long long G);
 int launch_wgrad(WgradParams& q, cudaStream_t st);   // fills q.S (number of partials actually written)
+bool wgrad_tc_supported(int M, int Cd);
+int launch_wgrad_tc(WgradParams& q, cudaStream_t st);   // tcgen05 version (bgemm_tc.cu), same contract
 
 struct MprojBwdParams {
   int Cin, J, P, K;    // J = 4 * nb rows of [conv_m1; conv_m2] per branch
