@@ -319,52 +319,101 @@ __global__ void __launch_bounds__(BT_NT, 2) wgrad_tc_kernel(WgradParams q, Wgrad
   umma::fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tslot), 0);
 
-  const int pi = tid & 15, rl = tid >> 4;            // position pair of the chunk, rows rl + 16 j
+  // position pair of the chunk and rows rl + 16 j.  A warp holds rows r and r + 4: with the 144-byte group pitch the
+  // two rows' 16-byte groups then fall on disjoint banks (rows r and r + 1 collide two-way)
+  const int pi = tid & 15, rl = (warp & 3) + 4 * ((tid >> 4) & 1) + 8 * (warp >> 2);
   float pa[8][2], pb[16][2];
-  auto pos_off = [&](const View4& w, long long gg) -> long long {
-    if (gg >= gend) return -1;
-    const int n = (int)(gg / PK);
-    const int j = (int)(gg - (long long)n * PK);
-    const int p = j / q.K, k = j - p * q.K;
-    return vix(w, n, 0, p, k);
-  };
+  // per-thread constants of the conversion: which of its rows exist, where the ones row sits, image offsets
+  uint32_t amask = 0, bmask = 0;
+  int onesj = -1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (i0 + rl + 16 * j < q.M) amask |= 1u << j;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int cc = c0 + rl + 16 * j;
+    if (j < NBJ && cc < q.Cd) {
+      if (cc == q.b_ones_row) onesj = j;
+      else bmask |= 1u << j;
+    }
+  }
+  const uint32_t soff0 = (uint32_t)umma::img16_off_b(rl, 2 * pi, (int)g.sbo), sstep = 2u * g.sbo;   // rows + 16
+  const bool al_a = !(q.a.sc & 1) && !(reinterpret_cast<uintptr_t>(q.a.p) & 7);
+  const bool al_b = !(q.b.sc & 1) && !(reinterpret_cast<uintptr_t>(q.b.p) & 7);
+  const long long astep = 16 * q.a.sc, bstep = 16 * q.b.sc;
+  // (sample, in-sample position) of this thread's first position, advanced by 32 per chunk: no 64-bit division in the loop
+  int pn, prem;
+  {
+    const long long gg = gbeg + 2 * pi;
+    pn = (int)(gg / PK);
+    prem = (int)(gg - (long long)pn * PK);
+  }
   auto load_chunk = [&](long long gc) {
     const long long gg = gc + 2 * pi;
-    const long long a0 = pos_off(q.a, gg), a1 = pos_off(q.a, gg + 1), b0 = pos_off(q.b, gg), b1 = pos_off(q.b, gg + 1);
-    const bool va = a0 >= 0 && a1 == a0 + 1 && !((a0 | q.a.sc) & 1) && !(reinterpret_cast<uintptr_t>(q.a.p) & 7);
-    const bool vb = b0 >= 0 && b1 == b0 + 1 && !((b0 | q.b.sc) & 1) && !(reinterpret_cast<uintptr_t>(q.b.p) & 7);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = i0 + rl + 16 * j;
-      pa[j][0] = pa[j][1] = 0.f;
-      if (i < q.M) {
-        if (va) {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(q.a.p + a0 + (long long)i * q.a.sc));
-          pa[j][0] = t.x;
-          pa[j][1] = t.y;
-        } else {
-          if (a0 >= 0) pa[j][0] = __ldg(q.a.p + a0 + (long long)i * q.a.sc);
-          if (a1 >= 0) pa[j][1] = __ldg(q.a.p + a1 + (long long)i * q.a.sc);
+    long long a0 = -1, a1 = -1, b0 = -1, b1 = -1;
+    if (gg < gend) {
+      const int p = prem / q.K, k = prem - p * q.K;
+      a0 = vix(q.a, pn, 0, p, k);
+      b0 = vix(q.b, pn, 0, p, k);
+      if (gg + 1 < gend) {
+        int n1 = pn, p1 = p, k1 = k + 1;
+        if (k1 == q.K) {
+          k1 = 0;
+          if (++p1 == q.P) {
+            p1 = 0;
+            ++n1;
+          }
         }
+        a1 = vix(q.a, n1, 0, p1, k1);
+        b1 = vix(q.b, n1, 0, p1, k1);
       }
     }
+    prem += WT_KC;
+    while (prem >= PK) {
+      prem -= PK;
+      ++pn;
+    }
+    if (al_a && a1 == a0 + 1 && !(a0 & 1)) {        // the common case: one 8-byte load per row, predicated, no branches
+      const float* ap = q.a.p + a0 + (long long)(i0 + rl) * q.a.sc;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int cc = c0 + rl + 16 * j;
-      pb[j][0] = pb[j][1] = 0.f;
-      if (j < NBJ && cc < q.Cd) {
-        if (cc == q.b_ones_row) {
+      for (int j = 0; j < 8; ++j) {
+        float2 t = make_float2(0.f, 0.f);
+        if ((amask >> j) & 1u) t = __ldg(reinterpret_cast<const float2*>(ap + j * astep));
+        pa[j][0] = t.x;
+        pa[j][1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long ro = (long long)(i0 + rl + 16 * j) * q.a.sc;
+        pa[j][0] = (((amask >> j) & 1u) && a0 >= 0) ? __ldg(q.a.p + a0 + ro) : 0.f;
+        pa[j][1] = (((amask >> j) & 1u) && a1 >= 0) ? __ldg(q.a.p + a1 + ro) : 0.f;
+      }
+    }
+    if (al_b && b1 == b0 + 1 && !(b0 & 1)) {
+      const float* bp = q.b.p + b0 + (long long)(c0 + rl) * q.b.sc;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float2 t = make_float2(0.f, 0.f);
+        if ((bmask >> j) & 1u) t = __ldg(reinterpret_cast<const float2*>(bp + j * bstep));
+        pb[j][0] = t.x;
+        pb[j][1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long ro = (long long)(c0 + rl + 16 * j) * q.b.sc;
+        pb[j][0] = (((bmask >> j) & 1u) && b0 >= 0) ? __ldg(q.b.p + b0 + ro) : 0.f;
+        pb[j][1] = (((bmask >> j) & 1u) && b1 >= 0) ? __ldg(q.b.p + b1 + ro) : 0.f;
+      }
+    }
+    if (onesj >= 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j == onesj) {
           pb[j][0] = b0 >= 0 ? 1.f : 0.f;
           pb[j][1] = b1 >= 0 ? 1.f : 0.f;
-        } else if (vb) {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(q.b.p + b0 + (long long)cc * q.b.sc));
-          pb[j][0] = t.x;
-          pb[j][1] = t.y;
-        } else {
-          if (b0 >= 0) pb[j][0] = __ldg(q.b.p + b0 + (long long)cc * q.b.sc);
-          if (b1 >= 0) pb[j][1] = __ldg(q.b.p + b1 + (long long)cc * q.b.sc);
         }
-      }
     }
   };
   if (gbeg < gend) load_chunk(gbeg);
@@ -381,7 +430,7 @@ __global__ void __launch_bounds__(BT_NT, 2) wgrad_tc_kernel(WgradParams q, Wgrad
       uint32_t h0, m0, l0, h1, m1, l1;
       umma::split_bf16x3(pa[j][0], h0, m0, l0);
       umma::split_bf16x3(pa[j][1], h1, m1, l1);
-      unsigned char* d = aimg + umma::img16_off_b(rl + 16 * j, 2 * pi, (int)g.sbo);
+      unsigned char* d = aimg + soff0 + (uint32_t)j * sstep;
       *reinterpret_cast<uint32_t*>(d) = umma::pack_bf16(h0, h1);
       *reinterpret_cast<uint32_t*>(d + g.a_plane) = umma::pack_bf16(m0, m1);
       *reinterpret_cast<uint32_t*>(d + 2 * g.a_plane) = umma::pack_bf16(l0, l1);
@@ -392,7 +441,7 @@ __global__ void __launch_bounds__(BT_NT, 2) wgrad_tc_kernel(WgradParams q, Wgrad
         uint32_t h0, m0, l0, h1, m1, l1;
         umma::split_bf16x3(pb[j][0], h0, m0, l0);
         umma::split_bf16x3(pb[j][1], h1, m1, l1);
-        unsigned char* d = bimg + umma::img16_off_b(rl + 16 * j, 2 * pi, (int)g.sbo);
+        unsigned char* d = bimg + soff0 + (uint32_t)j * sstep;
         *reinterpret_cast<uint32_t*>(d) = umma::pack_bf16(h0, h1);
         *reinterpret_cast<uint32_t*>(d + g.b_plane) = umma::pack_bf16(m0, m1);
         *reinterpret_cast<uint32_t*>(d + 2 * g.b_plane) = umma::pack_bf16(l0, l1);
