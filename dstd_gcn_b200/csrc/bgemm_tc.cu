@@ -128,24 +128,37 @@ __global__ void __launch_bounds__(BT_NT, 2) bgemm_tc_kernel(BgemmParams q, Bgemm
   const long long off0 = conv ? col_in[2 * pi] : -1, off1 = conv ? col_in[2 * pi + 1] : -1;
   const bool vec = off0 >= 0 && off1 == off0 + 1 && !((off0 | q.in.sc) & 1) && !(reinterpret_cast<uintptr_t>(q.in.p) & 7);
   float pv[PP][2];
+  const long long rstep = (long long)RSTEP * q.in.sc;
   auto load_chunk = [&](int c) {
+    const int kd0 = c * KC + r0;
+    uint32_t jm = 0;                                   // rows of this thread that exist in this chunk
 #pragma unroll
-    for (int j = 0; j < PP; ++j) {
-      const int kd = c * KC + r0 + RSTEP * j;
-      pv[j][0] = pv[j][1] = 0.f;
-      if (kd < q.Kd && r0 + RSTEP * j < KC) {
-        if (kd == q.ones_row) {
+    for (int j = 0; j < PP; ++j)
+      if (conv && kd0 + RSTEP * j < q.Kd && r0 + RSTEP * j < KC) jm |= 1u << j;
+    if (vec) {                                         // the common case: one predicated 8-byte load per row
+      const float* bp = q.in.p + off0 + (long long)kd0 * q.in.sc;
+#pragma unroll
+      for (int j = 0; j < PP; ++j) {
+        float2 t = make_float2(0.f, 0.f);
+        if ((jm >> j) & 1u) t = __ldg(reinterpret_cast<const float2*>(bp + j * rstep));
+        pv[j][0] = t.x;
+        pv[j][1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < PP; ++j) {
+        const long long ro = (long long)(kd0 + RSTEP * j) * q.in.sc;
+        pv[j][0] = (((jm >> j) & 1u) && off0 >= 0) ? __ldg(q.in.p + off0 + ro) : 0.f;
+        pv[j][1] = (((jm >> j) & 1u) && off1 >= 0) ? __ldg(q.in.p + off1 + ro) : 0.f;
+      }
+    }
+    if (q.ones_row >= 0) {
+#pragma unroll
+      for (int j = 0; j < PP; ++j)
+        if (((jm >> j) & 1u) && kd0 + RSTEP * j == q.ones_row) {
           pv[j][0] = off0 >= 0 ? 1.f : 0.f;
           pv[j][1] = off1 >= 0 ? 1.f : 0.f;
-        } else if (vec) {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(q.in.p + off0 + (long long)kd * q.in.sc));
-          pv[j][0] = t.x;
-          pv[j][1] = t.y;
-        } else {
-          if (off0 >= 0) pv[j][0] = __ldg(q.in.p + off0 + (long long)kd * q.in.sc);
-          if (off1 >= 0) pv[j][1] = __ldg(q.in.p + off1 + (long long)kd * q.in.sc);
         }
-      }
     }
   };
   load_chunk(0);
