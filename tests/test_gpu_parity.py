@@ -185,6 +185,14 @@ def test_gc_unit_abi_stress_shapes(case):
     assert _lib.load_library().dstd_gc_needs_xa(cin, cout, p, k, nb) == 1
 
 
+@pytest.mark.parametrize("case", [STRESS_CASES[4], STRESS_CASES[6]], ids=["ragged_tiles", "temporal_256"])
+def test_gc_unit_abi_wide_channels_cuda_core_gemm(case, monkeypatch):
+    """DSTD_BGEMM_TC=0: the wide channel mix and its weight gradient on the CUDA-core kernels (bgemm / wgrad of gemm.cu,
+    the fallback of bgemm_tc.cu) pass the same checks."""
+    monkeypatch.setenv("DSTD_BGEMM_TC", "0")
+    test_gc_unit_abi(case)
+
+
 def test_stress_config_model_vs_oracle():
     """BASELINE.json configs[4]: H3.6M joints, 50 -> 75 frames, 256 hidden channels (DSTDGCN(6, 50, 75, ., 22, 256, 5)):
     forward and every gradient against the fp64 oracle with the fp32 oracle as yardstick (same gates as the full-size
