@@ -365,7 +365,7 @@ def run_reference_arm(args):
     if args.cpu_seconds > 0:            # bound the CPU work: probe one step, then fit the sample into the budget
         _, sec1, _ = time_cpu_reference(args.workload, args.batch, 1, 1, threads)
         steps = max(2, min(args.steps, int(args.cpu_seconds / max(sec1, 1e-3))))
-        warm = 0
+        warm = 1                        # one untimed step on the engine that is timed (the probe ran on its own engine)
     sps, sec, kind = time_cpu_reference(args.workload, args.batch, steps, warm, threads)
     sps32, sec32, _ = time_cpu_reference(args.workload, 32, max(2, min(steps, 10)), 1, threads)
     what = ("unmodified reference (baseline/_ref) PredictionEngine.train" if kind == "reference" else "oracle port")
