@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(BT_NT, 2) bgemm_tc_kernel(BgemmParams q, Bgemm
     if (warp == 0) {
       ok &= umma::mbar_wait(&bar[buf], (uint32_t)use & 1u);    // weights of this chunk landed
       umma::fence_after();
-      const uint32_t a0 = abase + (uint32_t)buf * g.a_chunk, b0 = bbase + (uint32_t)buf * g.b_chunk;
+      // broadcast shuffles: ptxas then knows the stage bases are warp-uniform and keeps every descriptor word on the
+      // uniform datapath (without them: four R2UR moves in front of each MMA)
+      const uint32_t a0 = __shfl_sync(0xffffffffu, abase + (uint32_t)buf * g.a_chunk, 0);
+      const uint32_t b0 = __shfl_sync(0xffffffffu, bbase + (uint32_t)buf * g.b_chunk, 0);
       const uint32_t ahi = dhi(g.a_sbo), bhi = dhi(umma::IMG16_LBO_B);     // MN-major view: fields swapped
       const uint32_t leader = elect_lane();
       // consecutive instructions go to different accumulators (M tiles); small terms first: l*h, h*l, m*m, m*h, h*m, h*h
@@ -209,12 +212,16 @@ __global__ void __launch_bounds__(BT_NT, 2) bgemm_tc_kernel(BgemmParams q, Bgemm
           const uint32_t pa = (t == 0) ? 2u : (t == 2 || t == 3) ? 1u : 0u;      // plane of A: 0 = h, 1 = m, 2 = l
           const uint32_t pb = (t == 1) ? 2u : (t == 2 || t == 4) ? 1u : 0u;      // plane of B
           const uint32_t first = (c == 0 && s == 0 && t == 0) ? 0u : 1u;
-#pragma unroll 1
-          for (int mt = 0; mt < g.mtiles; ++mt) {
-            const uint32_t as = a0 + pa * g.a_plane + (uint32_t)(mt * 16) * g.a_sbo + (uint32_t)s * 2u * umma::IMG16_LBO_B;
-            const uint32_t bs = b0 + pb * g.b_plane + (uint32_t)s * 2u * g.b_sbo;
-            umma::mma_f16_lohi(tmem + (uint32_t)(mt * NP), dlo(as, umma::IMG16_LBO_B), ahi, dlo(bs, g.b_sbo), bhi, idesc, first,
-                               leader);
+          // fully unrolled over the (at most five) M tiles with a uniform guard: a run-time loop here makes ptxas carry
+          // the descriptor words in vector registers and pay ~9 R2UR moves in front of every MMA
+#pragma unroll
+          for (int mt = 0; mt < 5; ++mt) {
+            if (mt < g.mtiles) {
+              const uint32_t as = a0 + pa * g.a_plane + (uint32_t)(mt * 16) * g.a_sbo + (uint32_t)s * 2u * umma::IMG16_LBO_B;
+              const uint32_t bs = b0 + pb * g.b_plane + (uint32_t)s * 2u * g.b_sbo;
+              umma::mma_f16_lohi(tmem + (uint32_t)(mt * NP), dlo(as, umma::IMG16_LBO_B), ahi, dlo(bs, g.b_sbo), bhi, idesc, first,
+                                 leader);
+            }
           }
         }
       }
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(BT_NT, 2) wgrad_tc_kernel(WgradParams q, Wgrad
   };
   if (gbeg < gend) load_chunk(gbeg);
 
-  const uint32_t abase = umma::smem_u32(aimg), bbase = umma::smem_u32(bimg);
+  const uint32_t abase = __shfl_sync(0xffffffffu, umma::smem_u32(aimg), 0), bbase = __shfl_sync(0xffffffffu, umma::smem_u32(bimg), 0);
   const uint32_t idesc = umma::idesc_bf16(128, g.nbw, 0, 0);
   const uint32_t hi = dhi(g.sbo);
   bool ok = true;
