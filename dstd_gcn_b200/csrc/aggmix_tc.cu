@@ -253,18 +253,22 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
               mma_tf32_sync(acc[i], al, bh);
             }
           }
+          // tile offset = position part + channel part (tc_off): the channel part of this lane's two rows (c, c + 8) is
+          // computed once per tile, the position part once per column pair
+          {
+            const int c0 = m0 + fg;
+            const int cp0 = (c0 >> 2) * TC_LBO_F + (c0 & 3), cp1 = cp0 + 2 * TC_LBO_F;
+            const bool cok0 = c0 < Cin, cok1 = c0 + 8 < Cin;
 #pragma unroll
-          for (int i = 0; i < NTW; ++i) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = m0 + fg + 8 * (e >> 1), w = i * 8 + 2 * ft + (e & 1);
-              if (c < Cin && w < K) {
-                float hi, lo;
-                split_tf32(acc[i][e], hi, lo);
-                const int o = tc_off(l * K + w, c, sbo_f);
-                a_hi[o] = hi;
-                a_lo[o] = lo;
-              }
+            for (int i = 0; i < NTW; ++i) {
+              const int w0 = i * 8 + 2 * ft, r0 = l * K + w0, r1 = r0 + 1;
+              const int pp0 = (r0 >> 3) * sbo_f + ((r0 & 7) << 2), pp1 = (r1 >> 3) * sbo_f + ((r1 & 7) << 2);
+              const bool wok0 = w0 < K, wok1 = w0 + 1 < K;
+              float hi, lo;
+              if (cok0 && wok0) { split_tf32(acc[i][0], hi, lo); a_hi[pp0 + cp0] = hi; a_lo[pp0 + cp0] = lo; }
+              if (cok0 && wok1) { split_tf32(acc[i][1], hi, lo); a_hi[pp1 + cp0] = hi; a_lo[pp1 + cp0] = lo; }
+              if (cok1 && wok0) { split_tf32(acc[i][2], hi, lo); a_hi[pp0 + cp1] = hi; a_lo[pp0 + cp1] = lo; }
+              if (cok1 && wok1) { split_tf32(acc[i][3], hi, lo); a_hi[pp1 + cp1] = hi; a_lo[pp1 + cp1] = lo; }
             }
           }
         }
@@ -285,20 +289,31 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
+        // Warp-uniform issue: every lane of warp 0 runs the descriptor arithmetic (32-bit, on values made provably
+        // uniform by broadcast shuffles), one elected lane issues.  Issuing from `if (tid == 0)` kept the descriptors in
+        // vector registers and paid a chain of R2UR moves in front of each of the 27 small MMAs of a branch, with
+        // every other warp of the CTA waiting for the commit behind them.
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dah = tc_desc(smem_u32(a_hi), lbo_b, sbo_b), dal = tc_desc(smem_u32(a_lo), lbo_b, sbo_b);
-        const uint64_t dbh = tc_desc(smem_u32(b_img + (b * 2 + 0) * b_tile_f), lbo_b, sbo_b);
-        const uint64_t dbl = tc_desc(smem_u32(b_img + (b * 2 + 1) * b_tile_f), lbo_b, sbo_b);
-        for (int ks = 0; ks < KD / 8; ++ks) {
-          const uint64_t adv = (uint64_t)((ks * 2 * lbo_b) >> 4);   // 8 K-elements = two core matrices
-          umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, (b > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-          umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, 1u);   // lo*lo (2^-22 relative) is dropped: the MMA chain sits on
-                                                                // the item's critical path (every warp waits for the commit)
+        const uint32_t ua = __shfl_sync(0xffffffffu, smem_u32(a_hi), 0);
+        const uint32_t ub = __shfl_sync(0xffffffffu, smem_u32(b_img + (b * 2) * b_tile_f), 0);
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem_d, 0);
+        const uint32_t lof = (lbo_b >> 4) << 16, hiw = (sbo_b >> 4) | (1u << 14);
+        const uint32_t dah = ((ua & 0x3FFFFu) >> 4) | lof, dal = (((ua + (uint32_t)a_tile_f * 4u) & 0x3FFFFu) >> 4) | lof;
+        const uint32_t dbh = ((ub & 0x3FFFFu) >> 4) | lof, dbl = (((ub + (uint32_t)b_tile_f * 4u) & 0x3FFFFu) >> 4) | lof;
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(leader));
+        const int nks = KD / 8;
+#pragma unroll
+        for (int ks = 0; ks < 9; ++ks) {       // KD <= 72 (Cin <= 64)
+          if (ks < nks) {
+            const uint32_t adv = (uint32_t)ks * ((2u * lbo_b) >> 4);   // 8 K-elements = two core matrices
+            umma::mma_tf32_lohi(tm, dah + adv, hiw, dbh + adv, hiw, idesc, (b > 0 || ks > 0) ? 1u : 0u, leader);
+            umma::mma_tf32_lohi(tm, dah + adv, hiw, dbl + adv, hiw, idesc, 1u, leader);
+            umma::mma_tf32_lohi(tm, dal + adv, hiw, dbh + adv, hiw, idesc, 1u, leader);   // lo*lo (2^-22 relative) is dropped
+          }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
-                     : "memory");
+        umma::commit_elect(mbar);
       }
       // the A tile is rewritten by the next branch / item and TMEM is read by the epilogue only after the MMAs retire.
       // Only the issuing warp polls the mbarrier; the other 15 sleep at a block barrier (512 threads spinning on

@@ -172,6 +172,16 @@ __device__ __forceinline__ void mma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(b_hi), "r"(idesc), "r"(acc), "r"(leader)
       : "memory");
 }
+// kind::tf32 form of the same (descriptors as 32-bit halves, `leader` != 0 on the issuing lane)
+__device__ __forceinline__ void mma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t acc, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo),
+      "r"(b_hi), "r"(idesc), "r"(acc), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void commit_elect(uint64_t* mbar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
