@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
   // layer-skip chunk [Cout][XS_LD] (only when a skip is fused): staged with the lanes walking the SKIP tensor's own
   // contiguous direction, because the skip is kept in the other memory order (it is the block input)
   int* rowtab = reinterpret_cast<int*>(pdr + ((nb * PCH * KK + 3) & ~3));   // [nb*PCH*K]  (b*PCH + l) << 8 | v per row
-  float* sks = reinterpret_cast<float*>(rowtab + ((nb * PCH * K + 3) & ~3));
+  float* csum = reinterpret_cast<float*>(rowtab + ((nb * PCH * K + 3) & ~3));   // [nb*PCH*K]  column sums of xm (the bias row)
+  float* sks = csum + ((nb * PCH * K + 3) & ~3);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sks + (q.skip.p ? ((Cout * XS_LD + 3) & ~3) : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -146,6 +147,13 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
   uint32_t phase = 0;
   bool ok = true;
 
+  // optional per-phase cycle counters (-DDSTD_PHASE_TIMING, printed by CTA 0)
+#ifdef DSTD_PHASE_TIMING
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define TPH(i) do { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define TPH(i) do {} while (0)
+#endif
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int n = (int)(item / nchunk), p0 = (int)(item - (long long)n * nchunk) * PCH;
     const int pv = min(PCH, P - p0);
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
         pd_phase ^= 1;
       }
       __syncthreads();
+      TPH(0);   // staging
       // element-parallel; the row decode comes from a table built once per CTA (no runtime division in the loop)
       for (int i = tid; i < nb * PCH * K * KP; i += TC_NT) {
         const int row = i / KP, w = i - row * KP;
@@ -217,6 +226,44 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
         xms[i] = val;
       }
       __syncthreads();
+      // column sums of xm (they carry the conv_f bias through the ones row of the A tile) for every (branch, frame) at
+      // once: one thread per column, off the per-branch critical path (they were computed by four warps inside the
+      // branch loop, a 22-long dependent chain in front of every MMA issue)
+      for (int i = tid; i < nb * PCH * K; i += TC_NT) {
+        const int bl = i / K, w = i - bl * K;
+        const float* xm_l = xms + (bl * K) * KP + w;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four independent chains: the loads overlap
+        int v = 0;
+        for (; v + 4 <= K; v += 4) {
+          s0 += xm_l[v * KP];
+          s1 += xm_l[(v + 1) * KP];
+          s2 += xm_l[(v + 2) * KP];
+          s3 += xm_l[(v + 3) * KP];
+        }
+        for (; v < K; ++v) s0 += xm_l[v * KP];
+        csum[i] = (s0 + s1) + (s2 + s3);
+      }
+      // The tiles leave no room for a second staging buffer: pull the next item's chunk into L2 while this one computes,
+      // so that its cp.async staging pays L2 instead of HBM latency
+      {
+        const long long nxt = item + gridDim.x;
+        if (nxt < nitems) {
+          const int n2 = (int)(nxt / nchunk), q0 = (int)(nxt - (long long)n2 * nchunk) * PCH;
+          const int pv2 = min(PCH, P - q0);
+          auto pf_rows = [&](const float* base, long long row_stride, int rows, int run) {   // rows of `run` floats
+            const int lines = (run * 4 + 127) / 128 + 1;
+            for (int i = tid; i < rows * lines; i += TC_NT) {
+              const int r = i / lines, li = i - r * lines;
+              const float* a = base + (long long)r * row_stride + min(li * 32, run - 1);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+          };
+          if (q.x.sk == 1 && q.x.sp == K) pf_rows(q.x.p + (long long)n2 * q.x.sn + (long long)q0 * q.x.sp, q.x.sc, Cin, pv2 * K);
+          pf_rows(q.pd + ((long long)n2 * nb * P + q0) * KK, (long long)P * KK, nb, pv2 * KK);
+        }
+      }
+      __syncthreads();   // csum visible to the branch loop
+      TPH(1);   // adjacency transform
     }
 
     // ---- 2. per branch: aggregation into the UMMA A tile, then the tensor-core channel mix
@@ -272,23 +319,19 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
             }
           }
         }
-        // ones row (K index Cin): column sums of xm carry the conv_f bias; warp = frame, lane = w
-        for (int l = warp; l < pv; l += TC_NT / 32) {
-          const float* xm_l = xms + ((b * PCH + l) * K) * KP;
-          for (int w = lane; w < K; w += 32) {
-            float s = 0.f;
-            for (int v = 0; v < K; ++v) s += xm_l[v * KP + w];
-            float hi, lo;
-            split_tf32(s, hi, lo);
-            const int o = tc_off(l * K + w, Cin, sbo_f);
-            a_hi[o] = hi;
-            a_lo[o] = lo;
-          }
+        // ones row (K index Cin): the precomputed column sums of xm
+        for (int i = tid; i < pv * K; i += TC_NT) {
+          float hi, lo;
+          split_tf32(csum[b * PCH * K + i], hi, lo);
+          const int o = tc_off(i, Cin, sbo_f);
+          a_hi[o] = hi;
+          a_lo[o] = lo;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
+      TPH(2);   // aggregation + tile writes (+ fence, barrier)
       if (warp == 0) {
         // Warp-uniform issue: every lane of warp 0 runs the descriptor arithmetic (32-bit, on values made provably
         // uniform by broadcast shuffles), one elected lane issues.  Issuing from `if (tid == 0)` kept the descriptors in
@@ -322,6 +365,7 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
       ok = __syncthreads_and(ok);
       phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      TPH(3);   // MMA issue + wait for the commit
     }
 
     // ---- 3. epilogue: TMEM -> registers -> out (+ skip).  warp w: lanes 32 (w%4) .. +31 (positions), columns 16 (w/4) ..
@@ -356,8 +400,14 @@ __global__ void __launch_bounds__(TC_NT, 1) aggmix_fwd_tc_kernel(AggMixParams q,
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();   // TMEM drained and xs / xms / pdr free before the next item
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      TPH(4);   // epilogue
     }
   }
+#ifdef DSTD_PHASE_TIMING
+  if (blockIdx.x == 0 && tid == 0)
+    printf("aggmix_fwd_tc phases (cycles, CTA 0): stage %lld transform %lld aggregate %lld mma+wait %lld epilogue %lld\n", tph[0],
+           tph[1], tph[2], tph[3], tph[4]);
+#endif
   if (!ok && tid == 0 && err_flag) {
     *(volatile int*)err_flag = 1;
     __threadfence_system();
@@ -407,7 +457,7 @@ static bool tc_geom(int Cin, int Cout, int P, int K, int nb, TcGeom& g, bool wit
     if (pch > P && pch > 1) continue;
     const int XS_LD = ((pch * K + 3) / 8) * 8 + 4;
     size_t f = (size_t)2 * ((pch * K + 7) / 8) * sbo_f + g.wtc_floats + (size_t)((Cin * XS_LD + 3) & ~3) + (size_t)nb * pch * K * KP +
-               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + (size_t)((nb * pch * K + 3) & ~3) + 8 +
+               (size_t)((nb * K * K + 3) & ~3) + (size_t)((nb * pch * K * K + 3) & ~3) + (size_t)2 * ((nb * pch * K + 3) & ~3) + 8 +
                (with_skip ? (size_t)((Cout * XS_LD + 3) & ~3) : 0);
     // the M = 128 descriptors read 16 row groups from each A tile: keep that window inside the allocation
     const size_t a_window = (size_t)((pch * K + 7) / 8) * sbo_f + (size_t)16 * sbo_f + 64;
