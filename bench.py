@@ -708,12 +708,12 @@ def main():
             line["roofline"]["dominant_call"] = {"error": repr(e)}
         if world == 1 and not args.no_secondary:
             line["secondary"] = secondary
-        if not args.no_gpu_eager_baseline:
+        if world == 1 and not args.no_gpu_eager_baseline:       # baselines are single-GPU legs (rank 0, N = 1 only)
             try:
                 line["gpu_eager_baseline"] = time_gpu_eager_reference(args.workload, args.batch, min(args.steps, 10), 3)
             except Exception as e:
                 line["gpu_eager_baseline"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v_cpu, sec, kind = time_cpu_reference(args.workload, args.batch, args.cpu_baseline_steps, 1, threads)
             line["cpu_baseline"] = {"value": v_cpu, "unit": "samples/s", "cores": threads, "kind": kind,
