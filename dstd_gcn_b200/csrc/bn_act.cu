@@ -867,6 +867,10 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bn_bwd_apply_add_kernel(BnB
 //    bit-identical (tests/test_gpu_parity.py::test_bn_fast_path_equals_generic), the PReLU-slope partial is summed
 //    over a different thread mapping (equal to rounding).
 constexpr int BNF_MAXCH = 4;
+// BIG instantiations: slabs of 4097 .. 8192 positions (the stress configuration: two channels x T*V = 2750) with up to
+// 1024 threads, one CTA per SM, 13-bit slots (two channels at most, so the constant index still fits the word)
+constexpr int BNF_THREADS_BIG = 1024;
+template <bool BIG> struct BnfBits { static constexpr int SB = BIG ? 13 : 12; static constexpr uint32_t SM = (1u << SB) - 1u; };
 
 __device__ __forceinline__ void bnf_decode(bool tfast, int j, int T, int V, int TV, int& ch, int& t, int& v) {
   ch = j / TV;
@@ -884,15 +888,17 @@ __device__ __forceinline__ void bnf_timeout(int* err) {
 }
 
 // ---- forward apply: positions in out's memory order
-template <int NJ, int U, bool HAS_R, bool FULL>
-__device__ __forceinline__ void bnf_apply_consume(const float* st, const float4* ctab, const int (&pk)[NJ], float* ob,
+template <int NJ, int U, bool HAS_R, bool FULL, bool BIG>
+__device__ __forceinline__ void bnf_apply_consume(const float* st, const float4* ctab, const uint32_t (&pk)[NJ], float* ob,
                                                   long long osn, int CHTV, int left, float slope) {
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    if (pk[i] >= 0) {
-      const float4 k = ctab[pk[i] >> 24];
-      const float* py = st + (pk[i] & 0xfff);
-      const float* pr = st + U * CHTV + ((pk[i] >> 12) & 0xfff);
+    if ((int)(threadIdx.x + i * blockDim.x) < CHTV) {
+      constexpr int SB = BnfBits<BIG>::SB;
+      constexpr uint32_t SM = BnfBits<BIG>::SM;
+      const float4 k = ctab[pk[i] >> (2 * SB)];
+      const float* py = st + (pk[i] & SM);
+      const float* pr = st + U * CHTV + ((pk[i] >> SB) & SM);
       float* o = ob + i * blockDim.x;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -906,8 +912,8 @@ __device__ __forceinline__ void bnf_apply_consume(const float* st, const float4*
   }
 }
 
-template <int NJ, int U, bool HAS_R>
-__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_apply_kernel(BnFwdP q, int CH, int* err) {
+template <int NJ, int U, bool HAS_R, bool BIG>
+__global__ void __launch_bounds__(BIG ? BNF_THREADS_BIG : BN_THREADS_MAX, BIG ? 1 : 2) bnf_apply_kernel(BnFwdP q, int CH, int* err) {
   extern __shared__ __align__(16) float sh[];   // [2 stages][y (, r)][U][CH * T*V]
   __shared__ __align__(16) float4 ctab[BNF_MAXCH * 32];     // per (ch, v): mean, gamma * invstd, beta
   __shared__ double tot[32][2];
@@ -972,17 +978,19 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_apply_kernel(BnFwdP q, 
     }
     __syncthreads();
   }
-  int pk[NJ];   // slot in y's slab | slot in r's slab << 12 | (ch * 32 + v) << 24
+  uint32_t pk[NJ];   // slot in y's slab | slot in r's slab << SB | (ch * 32 + v) << 2 SB   (valid iff j < CHTV)
   {
+    constexpr int SB = BnfBits<BIG>::SB;
     const bool tf_o = t_fastest(q.out), tf_y = t_fastest(q.y), tf_r = HAS_R && t_fastest(q.r);
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       const int j = threadIdx.x + i * blockDim.x;
-      pk[i] = -1;
+      pk[i] = 0u;
       if (j < CHTV) {
         int ch, t, v;
         bnf_decode(tf_o, j, T, V, TV, ch, t, v);
-        pk[i] = (ch * TV + slot_of(tf_y, t, v, T, V)) | ((ch * TV + slot_of(tf_r, t, v, T, V)) << 12) | ((ch * 32 + v) << 24);
+        pk[i] = (uint32_t)(ch * TV + slot_of(tf_y, t, v, T, V)) | ((uint32_t)(ch * TV + slot_of(tf_r, t, v, T, V)) << SB) |
+                ((uint32_t)(ch * 32 + v) << (2 * SB));
       }
     }
   }
@@ -993,25 +1001,27 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_apply_kernel(BnFwdP q, 
     if (!umma::mbar_wait(&mbar[it & 1], (uint32_t)(it >> 1) & 1u)) bnf_timeout(err);
     const float* st = sh + (it & 1) * stage_f;
     const int left = n1 - (n0 + it * U);
-    if (left >= U) bnf_apply_consume<NJ, U, HAS_R, true>(st, ctab, pk, ob, osn, CHTV, left, slope);
-    else bnf_apply_consume<NJ, U, HAS_R, false>(st, ctab, pk, ob, osn, CHTV, left, slope);
+    if (left >= U) bnf_apply_consume<NJ, U, HAS_R, true, BIG>(st, ctab, pk, ob, osn, CHTV, left, slope);
+    else bnf_apply_consume<NJ, U, HAS_R, false, BIG>(st, ctab, pk, ob, osn, CHTV, left, slope);
     ob += U * osn;
     __syncthreads();
   }
 }
 
 // ---- backward pass 1: positions in y's memory order
-template <int NJ, int U, bool USE_R, bool FULL>
-__device__ __forceinline__ void bnf_reduce_consume(const float* st, const float4* ctab, const int (&pk)[NJ], int CHTV,
+template <int NJ, int U, bool USE_R, bool FULL, bool BIG>
+__device__ __forceinline__ void bnf_reduce_consume(const float* st, const float4* ctab, const uint32_t (&pk)[NJ], int CHTV,
                                                    int left, float slope, bool has_prelu, float (&a1)[NJ],
                                                    float (&a2)[NJ], float& gsl) {
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    if (pk[i] >= 0) {
-      const float4 k = ctab[pk[i] >> 24];
-      const float* pg = st + (pk[i] & 0xfff);
+    if ((int)(threadIdx.x + i * blockDim.x) < CHTV) {
+      constexpr int SB = BnfBits<BIG>::SB;
+      constexpr uint32_t SM = BnfBits<BIG>::SM;
+      const float4 k = ctab[pk[i] >> (2 * SB)];
+      const float* pg = st + (pk[i] & SM);
       const float* py = st + U * CHTV + threadIdx.x + i * blockDim.x;
-      const float* pr = st + 2 * U * CHTV + ((pk[i] >> 12) & 0xfff);
+      const float* pr = st + 2 * U * CHTV + ((pk[i] >> SB) & SM);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (FULL || u < left) {
@@ -1027,8 +1037,8 @@ __device__ __forceinline__ void bnf_reduce_consume(const float* st, const float4
   }
 }
 
-template <int NJ, int U, bool USE_R>
-__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_reduce_kernel(BnBwdP q, int CH, int* err) {
+template <int NJ, int U, bool USE_R, bool BIG>
+__global__ void __launch_bounds__(BIG ? BNF_THREADS_BIG : BN_THREADS_MAX, BIG ? 1 : 2) bnf_bwd_reduce_kernel(BnBwdP q, int CH, int* err) {
   extern __shared__ __align__(16) float sh[];   // [2 stages][gout, y (, r)][U][CH * T*V]
   __shared__ __align__(16) float4 ctab[BNF_MAXCH * 32];     // per (ch, v): mean, invstd, gamma, beta
   __shared__ float red[32];
@@ -1064,20 +1074,22 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_reduce_kernel(BnBwd
     }
   };
   if (threadIdx.x == 0 && iters > 0) issue(0);
-  int pk[NJ];   // slot in gout's slab | slot in r's slab << 12 | (ch * 32 + v) << 24;  y is read at j itself
+  uint32_t pk[NJ];   // slot in gout's slab | slot in r's slab << SB | (ch * 32 + v) << 2 SB;  y is read at j itself
   float a1[NJ], a2[NJ], gsl = 0.f;
   const bool tf_y = t_fastest(q.y);
   {
+    constexpr int SB = BnfBits<BIG>::SB;
     const bool tf_g = t_fastest(q.gout), tf_r = USE_R && t_fastest(q.r);
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       const int j = threadIdx.x + i * blockDim.x;
-      pk[i] = -1;
+      pk[i] = 0u;
       a1[i] = a2[i] = 0.f;
       if (j < CHTV) {
         int ch, t, v;
         bnf_decode(tf_y, j, T, V, TV, ch, t, v);
-        pk[i] = (ch * TV + slot_of(tf_g, t, v, T, V)) | ((ch * TV + slot_of(tf_r, t, v, T, V)) << 12) | ((ch * 32 + v) << 24);
+        pk[i] = (uint32_t)(ch * TV + slot_of(tf_g, t, v, T, V)) | ((uint32_t)(ch * TV + slot_of(tf_r, t, v, T, V)) << SB) |
+                ((uint32_t)(ch * 32 + v) << (2 * SB));
       }
     }
   }
@@ -1086,8 +1098,8 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_reduce_kernel(BnBwd
     if (!umma::mbar_wait(&mbar[it & 1], (uint32_t)(it >> 1) & 1u)) bnf_timeout(err);
     const float* st = sh + (it & 1) * stage_f;
     const int left = n1 - (n0 + it * U);
-    if (left >= U) bnf_reduce_consume<NJ, U, USE_R, true>(st, ctab, pk, CHTV, left, slope, has_prelu, a1, a2, gsl);
-    else bnf_reduce_consume<NJ, U, USE_R, false>(st, ctab, pk, CHTV, left, slope, has_prelu, a1, a2, gsl);
+    if (left >= U) bnf_reduce_consume<NJ, U, USE_R, true, BIG>(st, ctab, pk, CHTV, left, slope, has_prelu, a1, a2, gsl);
+    else bnf_reduce_consume<NJ, U, USE_R, false, BIG>(st, ctab, pk, CHTV, left, slope, has_prelu, a1, a2, gsl);
     __syncthreads();
   }
   // per-(c,v) totals: positions to their logical slot, then one thread per (ch, v) sums over t in order (fp64)
@@ -1118,20 +1130,22 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_reduce_kernel(BnBwd
 }
 
 // ---- backward pass 2: positions in gy's memory order; gr (same order as gy) is stored straight from registers
-template <int NJ, int U, bool USE_R, bool HAS_GR, bool ADD, bool FULL>
+template <int NJ, int U, bool USE_R, bool HAS_GR, bool ADD, bool FULL, bool BIG>
 __device__ __forceinline__ void bnf_bwd_apply_consume(const float* st, const float4* ctab, const float4* ctab2,
-                                                      const int (&pk)[NJ], const int (&pk2)[NJ], float* gyb, float* grb,
+                                                      const uint32_t (&pk)[NJ], const uint32_t (&pk2)[NJ], float* gyb, float* grb,
                                                       long long gysn, long long grsn, int CHTV, int left, float slope,
                                                       bool has_prelu) {
   constexpr int ADD_REGION = USE_R ? 3 : 2;
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    if (pk[i] >= 0) {
-      const float4 k = ctab[pk[i] >> 24], k2 = ctab2[pk[i] >> 24];
-      const float* pg = st + (pk[i] & 0xfff);
-      const float* py = st + U * CHTV + ((pk[i] >> 12) & 0xfff);
-      const float* pr = st + 2 * U * CHTV + (pk2[i] & 0xfff);
-      const float* pa = st + ADD_REGION * U * CHTV + ((pk2[i] >> 12) & 0xfff);
+    if ((int)(threadIdx.x + i * blockDim.x) < CHTV) {
+      constexpr int SB = BnfBits<BIG>::SB;
+      constexpr uint32_t SM = BnfBits<BIG>::SM;
+      const float4 k = ctab[pk[i] >> (2 * SB)], k2 = ctab2[pk[i] >> (2 * SB)];
+      const float* pg = st + (pk[i] & SM);
+      const float* py = st + U * CHTV + ((pk[i] >> SB) & SM);
+      const float* pr = st + 2 * U * CHTV + (pk2[i] & SM);
+      const float* pa = st + ADD_REGION * U * CHTV + ((pk2[i] >> SB) & SM);
       float* o = gyb + i * blockDim.x;
       float* o2 = grb + i * blockDim.x;
 #pragma unroll
@@ -1148,8 +1162,8 @@ __device__ __forceinline__ void bnf_bwd_apply_consume(const float* st, const flo
   }
 }
 
-template <int NJ, int U, bool USE_R, bool HAS_GR, bool ADD>
-__global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_apply_kernel(BnBwdP q, int CH, int NP, int* err) {
+template <int NJ, int U, bool USE_R, bool HAS_GR, bool ADD, bool BIG>
+__global__ void __launch_bounds__(BIG ? BNF_THREADS_BIG : BN_THREADS_MAX, BIG ? 1 : 2) bnf_bwd_apply_kernel(BnBwdP q, int CH, int NP, int* err) {
   extern __shared__ __align__(16) float sh[];   // [2 stages][gout, y (, r) (, gr_add)][U][CH * T*V]
   __shared__ __align__(16) float4 ctab[BNF_MAXCH * 32];     // mean, invstd, gamma, beta
   __shared__ __align__(16) float4 ctab2[BNF_MAXCH * 32];    // gamma * invstd, k1, k2
@@ -1212,20 +1226,22 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_apply_kernel(BnBwdP
     }
     __syncthreads();
   }
-  int pk[NJ], pk2[NJ];   // gout slot | y slot << 12 | (ch*32+v) << 24;   r slot | gr_add slot << 12
+  uint32_t pk[NJ], pk2[NJ];   // gout slot | y slot << SB | (ch*32+v) << 2 SB;   r slot | gr_add slot << SB
   {
+    constexpr int SB = BnfBits<BIG>::SB;
     const bool tf_o = t_fastest(q.gy), tf_g = t_fastest(q.gout), tf_y = t_fastest(q.y), tf_r = USE_R && t_fastest(q.r),
                tf_a = ADD && t_fastest(q.gadd);
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       const int j = threadIdx.x + i * blockDim.x;
-      pk[i] = -1;
-      pk2[i] = 0;
+      pk[i] = 0u;
+      pk2[i] = 0u;
       if (j < CHTV) {
         int ch, t, v;
         bnf_decode(tf_o, j, T, V, TV, ch, t, v);
-        pk[i] = (ch * TV + slot_of(tf_g, t, v, T, V)) | ((ch * TV + slot_of(tf_y, t, v, T, V)) << 12) | ((ch * 32 + v) << 24);
-        pk2[i] = (ch * TV + slot_of(tf_r, t, v, T, V)) | ((ch * TV + slot_of(tf_a, t, v, T, V)) << 12);
+        pk[i] = (uint32_t)(ch * TV + slot_of(tf_g, t, v, T, V)) | ((uint32_t)(ch * TV + slot_of(tf_y, t, v, T, V)) << SB) |
+                ((uint32_t)(ch * 32 + v) << (2 * SB));
+        pk2[i] = (uint32_t)(ch * TV + slot_of(tf_r, t, v, T, V)) | ((uint32_t)(ch * TV + slot_of(tf_a, t, v, T, V)) << SB);
       }
     }
   }
@@ -1238,9 +1254,9 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_apply_kernel(BnBwdP
     const float* st = sh + (it & 1) * stage_f;
     const int left = n1 - (n0 + it * U);
     if (left >= U)
-      bnf_bwd_apply_consume<NJ, U, USE_R, HAS_GR, ADD, true>(st, ctab, ctab2, pk, pk2, gyb, grb, gysn, grsn, CHTV, left, slope, has_prelu);
+      bnf_bwd_apply_consume<NJ, U, USE_R, HAS_GR, ADD, true, BIG>(st, ctab, ctab2, pk, pk2, gyb, grb, gysn, grsn, CHTV, left, slope, has_prelu);
     else
-      bnf_bwd_apply_consume<NJ, U, USE_R, HAS_GR, ADD, false>(st, ctab, ctab2, pk, pk2, gyb, grb, gysn, grsn, CHTV, left, slope, has_prelu);
+      bnf_bwd_apply_consume<NJ, U, USE_R, HAS_GR, ADD, false, BIG>(st, ctab, ctab2, pk, pk2, gyb, grb, gysn, grsn, CHTV, left, slope, has_prelu);
     gyb += U * gysn;
     if (HAS_GR) grb += U * grsn;
     __syncthreads();
@@ -1251,6 +1267,7 @@ __global__ void __launch_bounds__(BN_THREADS_MAX, 2) bnf_bwd_apply_kernel(BnBwdP
 struct BnFastPlan {
   bool ok;
   int ch, nj, threads;
+  bool big;     // slab of 4097 .. 8192 positions: BIG instantiations (<= 1024 threads, one CTA per SM)
 };
 static bool bnf_tfast(const View4& w) { return !(w.sk == 1 || w.sp != 1); }
 static bool bnf_slab_ok(const View4& w, int T, int V) {
@@ -1259,14 +1276,15 @@ static bool bnf_slab_ok(const View4& w, int T, int V) {
   return dense && w.sc == (long long)T * V && (reinterpret_cast<unsigned long long>(w.p) & 15ull) == 0 && (w.sn & 3ll) == 0;
 }
 static BnFastPlan bnf_plan(int C, int T, int V, const float* mask, std::initializer_list<const View4*> ws) {
-  BnFastPlan pl{false, 0, 0, 0};
+  BnFastPlan pl{false, 0, 0, 0, false};
   const char* e = getenv("DSTD_BN_FAST");          // read per call: the tests compare both paths
   if (e && atoi(e) == 0) return pl;
   if (mask || V > 32) return pl;
   const int TV = T * V;
   pl.ch = (TV % 4 == 0) ? 1 : (TV % 2 == 0) ? 2 : 4;
   const int chtv = pl.ch * TV;
-  if (C % pl.ch || chtv > 4096) return pl;
+  pl.big = chtv > 4096;
+  if (C % pl.ch || chtv > 8 * BNF_THREADS_BIG || (pl.big && pl.ch > 2)) return pl;
   for (const View4* w : ws)
     if (!bnf_slab_ok(*w, T, V)) return pl;
   pl.nj = chtv <= 4 * BN_THREADS_MAX ? 4 : 8;
@@ -1275,32 +1293,33 @@ static BnFastPlan bnf_plan(int C, int T, int V, const float* mask, std::initiali
   return pl;
 }
 // samples per stage: the largest of 4/2/1 whose two stages of `nst` slabs fit two CTAs per SM; 0 = none
-static int bnf_pick_u(size_t slab_bytes, int nst) {
-  for (int u = 4; u >= 1; u >>= 1)
-    if ((size_t)2 * nst * u * slab_bytes <= BN_SMEM_BUDGET) return u;
+static int bnf_pick_u(size_t slab_bytes, int nst, bool big = false) {
+  const size_t budget = big ? (size_t)220 * 1024 : BN_SMEM_BUDGET;   // BIG: one CTA per SM
+  for (int u = big ? 2 : 4; u >= 1; u >>= 1)
+    if ((size_t)2 * nst * u * slab_bytes <= budget) return u;
   return 0;
 }
 
+#define DSTD_BNF_ONE(KERN, NJ_, U_, BIG_, grid, threads, smem, st, ...)                               \
+  do {                                                                                                \
+    prefer_smem_carveout((const void*)KERN(NJ_, U_, BIG_), true);                                     \
+    KERN(NJ_, U_, BIG_)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                    \
+  } while (0)
 #define DSTD_BNF_U(KERN, NJ_, u, grid, threads, smem, st, ...)                                        \
   do {                                                                                                \
     switch (u) {                                                                                      \
-      case 4:                                                                                         \
-        prefer_smem_carveout((const void*)KERN(NJ_, 4), true);                                        \
-        KERN(NJ_, 4)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                       \
-        break;                                                                                        \
-      case 2:                                                                                         \
-        prefer_smem_carveout((const void*)KERN(NJ_, 2), true);                                        \
-        KERN(NJ_, 2)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                       \
-        break;                                                                                        \
-      default:                                                                                        \
-        prefer_smem_carveout((const void*)KERN(NJ_, 1), true);                                        \
-        KERN(NJ_, 1)<<<grid, threads, smem, st>>>(__VA_ARGS__);                                       \
-        break;                                                                                        \
+      case 4: DSTD_BNF_ONE(KERN, NJ_, 4, false, grid, threads, smem, st, __VA_ARGS__); break;         \
+      case 2: DSTD_BNF_ONE(KERN, NJ_, 2, false, grid, threads, smem, st, __VA_ARGS__); break;         \
+      default: DSTD_BNF_ONE(KERN, NJ_, 1, false, grid, threads, smem, st, __VA_ARGS__); break;        \
     }                                                                                                 \
   } while (0)
-#define DSTD_BNF(KERN, nj, u, grid, threads, smem, st, ...)                                           \
+// plan: {nj, big}; BIG slabs always run 8 positions per thread, 2 or 1 samples per stage
+#define DSTD_BNF(KERN, plan, u, grid, threads, smem, st, ...)                                         \
   do {                                                                                                \
-    if ((nj) == 4) DSTD_BNF_U(KERN, 4, u, grid, threads, smem, st, __VA_ARGS__);                      \
+    if ((plan).big) {                                                                                 \
+      if ((u) == 2) DSTD_BNF_ONE(KERN, 8, 2, true, grid, threads, smem, st, __VA_ARGS__);             \
+      else DSTD_BNF_ONE(KERN, 8, 1, true, grid, threads, smem, st, __VA_ARGS__);                      \
+    } else if ((plan).nj == 4) DSTD_BNF_U(KERN, 4, u, grid, threads, smem, st, __VA_ARGS__);          \
     else DSTD_BNF_U(KERN, 8, u, grid, threads, smem, st, __VA_ARGS__);                                \
   } while (0)
 
@@ -1396,15 +1415,15 @@ extern "C" int dstd_bn_act_forward(const dstd_bn_act_fwd_args* a, dstd_stream_t 
     DSTD_LAUNCH_CHECK("bn_eval_stats");
   }
   const BnFastPlan fp = bnf_plan(q.C, q.T, q.V, q.mask, {&q.y, &q.r, &q.out});
-  const int fu = fp.ok ? bnf_pick_u((size_t)fp.ch * tvb, nst) : 0;
+  const int fu = fp.ok ? bnf_pick_u((size_t)fp.ch * tvb, nst, fp.big) : 0;
   if (fu) {   // bulk-copy staged kernel (see "fast path")
     const dim3 grid(q.C / fp.ch, q.S);
     const size_t smem = (size_t)2 * nst * fu * fp.ch * tvb;
     int* err = device_error_word();
-#define DSTD_K_APPLY_R(NJ_, U_) bnf_apply_kernel<NJ_, U_, true>
-#define DSTD_K_APPLY(NJ_, U_) bnf_apply_kernel<NJ_, U_, false>
-    if (q.r.p) DSTD_BNF(DSTD_K_APPLY_R, fp.nj, fu, grid, fp.threads, smem, st, q, fp.ch, err);
-    else DSTD_BNF(DSTD_K_APPLY, fp.nj, fu, grid, fp.threads, smem, st, q, fp.ch, err);
+#define DSTD_K_APPLY_R(NJ_, U_, B_) bnf_apply_kernel<NJ_, U_, true, B_>
+#define DSTD_K_APPLY(NJ_, U_, B_) bnf_apply_kernel<NJ_, U_, false, B_>
+    if (q.r.p) DSTD_BNF(DSTD_K_APPLY_R, fp, fu, grid, fp.threads, smem, st, q, fp.ch, err);
+    else DSTD_BNF(DSTD_K_APPLY, fp, fu, grid, fp.threads, smem, st, q, fp.ch, err);
 #undef DSTD_K_APPLY_R
 #undef DSTD_K_APPLY
     count_launch();
@@ -1449,28 +1468,28 @@ extern "C" int dstd_bn_act_backward(const dstd_bn_act_bwd_args* a, dstd_stream_t
     const bool combo = use_r ? has_gr : (!has_gr && !add);     // the instantiations the model uses
     const bool gr_same = !has_gr || bnf_tfast(q.gr) == bnf_tfast(q.gy);
     const BnFastPlan fp = (combo && gr_same) ? bnf_plan(q.C, q.T, q.V, q.mask, {&q.y, &q.r, &q.gout, &q.gy, &q.gr, &q.gadd})
-                                             : BnFastPlan{false, 0, 0, 0};
-    const int u1 = fp.ok ? bnf_pick_u((size_t)fp.ch * tv, nst) : 0;
-    const int u2 = fp.ok ? bnf_pick_u((size_t)fp.ch * tv, nst + (add ? 1 : 0)) : 0;
+                                             : BnFastPlan{false, 0, 0, 0, false};
+    const int u1 = fp.ok ? bnf_pick_u((size_t)fp.ch * tv, nst, fp.big) : 0;
+    const int u2 = fp.ok ? bnf_pick_u((size_t)fp.ch * tv, nst + (add ? 1 : 0), fp.big) : 0;
     if (u1 && u2) {
       const dim3 grid(q.C / fp.ch, q.S);
       int* err = device_error_word();
-#define DSTD_K_RED_R(NJ_, U_) bnf_bwd_reduce_kernel<NJ_, U_, true>
-#define DSTD_K_RED(NJ_, U_) bnf_bwd_reduce_kernel<NJ_, U_, false>
-      if (use_r) DSTD_BNF(DSTD_K_RED_R, fp.nj, u1, grid, fp.threads, (size_t)2 * nst * u1 * fp.ch * tv, st, q, fp.ch, err);
-      else DSTD_BNF(DSTD_K_RED, fp.nj, u1, grid, fp.threads, (size_t)2 * nst * u1 * fp.ch * tv, st, q, fp.ch, err);
+#define DSTD_K_RED_R(NJ_, U_, B_) bnf_bwd_reduce_kernel<NJ_, U_, true, B_>
+#define DSTD_K_RED(NJ_, U_, B_) bnf_bwd_reduce_kernel<NJ_, U_, false, B_>
+      if (use_r) DSTD_BNF(DSTD_K_RED_R, fp, u1, grid, fp.threads, (size_t)2 * nst * u1 * fp.ch * tv, st, q, fp.ch, err);
+      else DSTD_BNF(DSTD_K_RED, fp, u1, grid, fp.threads, (size_t)2 * nst * u1 * fp.ch * tv, st, q, fp.ch, err);
 #undef DSTD_K_RED_R
 #undef DSTD_K_RED
       count_launch();
       DSTD_LAUNCH_CHECK("bnf_bwd_reduce");
       const int np = (int)(grid.x * grid.y);
       const size_t smem2 = (size_t)2 * (nst + (add ? 1 : 0)) * u2 * fp.ch * tv;
-#define DSTD_K_APP_RA(NJ_, U_) bnf_bwd_apply_kernel<NJ_, U_, true, true, true>
-#define DSTD_K_APP_R(NJ_, U_) bnf_bwd_apply_kernel<NJ_, U_, true, true, false>
-#define DSTD_K_APP(NJ_, U_) bnf_bwd_apply_kernel<NJ_, U_, false, false, false>
-      if (use_r && add) DSTD_BNF(DSTD_K_APP_RA, fp.nj, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
-      else if (use_r) DSTD_BNF(DSTD_K_APP_R, fp.nj, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
-      else DSTD_BNF(DSTD_K_APP, fp.nj, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
+#define DSTD_K_APP_RA(NJ_, U_, B_) bnf_bwd_apply_kernel<NJ_, U_, true, true, true, B_>
+#define DSTD_K_APP_R(NJ_, U_, B_) bnf_bwd_apply_kernel<NJ_, U_, true, true, false, B_>
+#define DSTD_K_APP(NJ_, U_, B_) bnf_bwd_apply_kernel<NJ_, U_, false, false, false, B_>
+      if (use_r && add) DSTD_BNF(DSTD_K_APP_RA, fp, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
+      else if (use_r) DSTD_BNF(DSTD_K_APP_R, fp, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
+      else DSTD_BNF(DSTD_K_APP, fp, u2, grid, fp.threads, smem2, st, q, fp.ch, np, err);
 #undef DSTD_K_APP_RA
 #undef DSTD_K_APP_R
 #undef DSTD_K_APP

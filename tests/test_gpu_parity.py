@@ -316,6 +316,8 @@ BN_FAST_CASES = [
     (5, 8, 35, 25, "t", "t", 2, True, True),      # CMU plane (875: four channels per slab)
     (5, 8, 35, 25, "v", None, 1, True, False),    # eval mode
     (3, 4, 10, 22, "t", None, 0, False, True),    # no PReLU, output like the input
+    (5, 4, 125, 22, "t", "t", 2, True, True),     # stress plane (2750: two channels per slab = 5500 positions, BIG variant)
+    (3, 4, 125, 22, "v", None, 1, True, True),    # stress layer BN
 ]
 
 
