@@ -5,6 +5,8 @@
 // (deterministic).  The pairwise tanh tensor D (2750 KB per sample at the stress shape) is produced and consumed in
 // (k', pair) tiles and never leaves the SM; the channel contraction of these shapes runs in bgemm / wgrad (gemm.cu).
 //   limits: P <= 128, K <= 128.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace dstd {
@@ -396,8 +398,113 @@ __global__ void __launch_bounds__(256) aggregate_fwd_gen_kernel(AggParams q) {
   }
 }
 
+// ---- tensor-path forward aggregation (mma.sync m16n8k8 TF32 with 3xTF32 compensation), K >= 48.
+// The CUDA-core kernel above is bound by shared-memory wavefronts: every warp re-reads the whole K x K adjacency (four
+// wavefronts per v) for 32 FFMAs, 24 wavefronts per 128 FFMAs against the 16 FFMAs per wavefront that four schedulers
+// need (measured 29 % FMA utilisation).  Here a warp owns a 16-channel tile x all w columns (C fragments), the A
+// fragments (x) come straight from global memory in fragment layout (a quad reads 16 contiguous bytes of a channel row,
+// the k + 4 half is the other half of the same sector), the B fragments (xm) from shared memory with a row stride of
+// 8 (mod 32) floats: one B fragment feeds 3 MMAs = 2048 MACs per two shared-memory loads.
+__device__ __forceinline__ void ag_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void ag_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__host__ __device__ inline int agm_kld(int K) { return ((K + 31) & ~31) + 8; }   // == 8 (mod 32): conflict-free B fragments
+
+template <int NT>   // 8-column tiles of w: 8 NT >= K
+__global__ void __launch_bounds__(256) aggregate_fwd_gen_mma_kernel(AggParams q) {
+  extern __shared__ __align__(16) float smem[];
+  const int K = q.K, P = q.P, Cin = q.Cin, C1 = Cin + 1, KP8 = (K + 7) & ~7, KLD = agm_kld(K);
+  float* xm = smem;                          // [KP8][KLD]   xmu[v][w], zero padded
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fg = lane >> 2, ft = lane & 3;
+  const int p = blockIdx.x, n = blockIdx.y;
+  const float alpha = q.alpha ? __ldg(q.alpha) : 1.0f;
+  const float* xb = q.x.p + vix(q.x, n, 0, p, 0);
+  const int mtiles = (C1 + 15) >> 4;
+  for (int b = 0; b < q.nb; ++b) {
+    __syncthreads();                         // every warp is done with the previous branch's xm
+    ag_build_xm(q, n, b, p, alpha, xm, KP8, KLD);
+    __syncthreads();
+    for (int mt = warp; mt < mtiles; mt += 8) {
+      const int c0 = mt * 16 + fg, c1 = c0 + 8;
+      // row sources of this lane: a channel row of x, the ones row (c == Cin) or nothing
+      const float* r0 = c0 < Cin ? xb + (long long)c0 * q.x.sc : nullptr;
+      const float* r1 = c1 < Cin ? xb + (long long)c1 * q.x.sc : nullptr;
+      const float one0 = c0 == Cin ? 1.f : 0.f, one1 = c1 == Cin ? 1.f : 0.f;
+      float acc[NT][4];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      auto lda = [&](int k0, float (&a)[4]) {
+        const int v0 = k0 + ft, v1 = v0 + 4;
+        a[0] = v0 < K ? (r0 ? __ldg(r0 + (long long)v0 * q.x.sk) : one0) : 0.f;
+        a[1] = v0 < K ? (r1 ? __ldg(r1 + (long long)v0 * q.x.sk) : one1) : 0.f;
+        a[2] = v1 < K ? (r0 ? __ldg(r0 + (long long)v1 * q.x.sk) : one0) : 0.f;
+        a[3] = v1 < K ? (r1 ? __ldg(r1 + (long long)v1 * q.x.sk) : one1) : 0.f;
+      };
+      float an[4];
+      lda(0, an);
+      for (int k0 = 0; k0 < KP8; k0 += 8) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ag_split(an[e], ah[e], al[e]);
+        if (k0 + 8 < KP8) lda(k0 + 8, an);   // next k-step's fragment in flight during this one's MMAs
+        const float* br = xm + (k0 + ft) * KLD + fg;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          uint32_t bh[2], bl[2];
+          ag_split(br[i * 8], bh[0], bl[0]);
+          ag_split(br[4 * KLD + i * 8], bh[1], bl[1]);
+          ag_mma(acc[i], al, bh);
+          ag_mma(acc[i], ah, bl);
+          ag_mma(acc[i], ah, bh);
+        }
+      }
+      float* d0 = q.xa + (((long long)(n * q.nb + b) * C1 + c0) * P + p) * K;
+      float* d1 = q.xa + (((long long)(n * q.nb + b) * C1 + c1) * P + p) * K;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const int w = i * 8 + 2 * ft;
+        if (c0 < C1) {
+          if (w < K) d0[w] = acc[i][0];
+          if (w + 1 < K) d0[w + 1] = acc[i][1];
+        }
+        if (c1 < C1) {
+          if (w < K) d1[w] = acc[i][2];
+          if (w + 1 < K) d1[w + 1] = acc[i][3];
+        }
+      }
+    }
+  }
+}
+
+static bool agg_gen_mma_on(int K) {
+  const char* e = getenv("DSTD_AGG_GEN_MMA");          // read per call (A/B in the tests)
+  const bool on = e ? atoi(e) != 0 : false;
+  return on && K >= 48;
+}
+
 int launch_aggregate_fwd_gen(const AggParams& q, cudaStream_t st) {
   DSTD_REQUIRE(generic_supported(q.P, q.K), DSTD_ERR_UNSUPPORTED, "aggregate_fwd_gen: P=%d K=%d outside limits", q.P, q.K);
+  if (agg_gen_mma_on(q.K)) {
+    const int KP8 = (q.K + 7) & ~7, KLD = agm_kld(q.K);
+    const size_t sm = (size_t)KP8 * KLD * sizeof(float);
+    dim3 grid(q.P, q.N);
+#define DSTD_AGM(NT_)                                                         \
+  {                                                                           \
+    ensure_max_smem((const void*)aggregate_fwd_gen_mma_kernel<NT_>);          \
+    aggregate_fwd_gen_mma_kernel<NT_><<<grid, 256, sm, st>>>(q);              \
+  }
+    const int nt = (q.K + 7) / 8;
+    if (nt <= 8) DSTD_AGM(8) else if (nt <= 12) DSTD_AGM(12) else DSTD_AGM(16)
+#undef DSTD_AGM
+    count_launch();
+    return check_launch("aggregate_fwd_gen_mma");
+  }
   const int KP4 = ag_kp4(q.K), KL = ag_kl(q.K);
   const size_t smem = ((size_t)((KP4 * KL + 3) & ~3) + (size_t)8 * AG_CW * KP4) * sizeof(float);
   dim3 grid(q.P, q.N);

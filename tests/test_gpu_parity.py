@@ -193,6 +193,13 @@ def test_gc_unit_abi_wide_channels_cuda_core_gemm(case, monkeypatch):
     test_gc_unit_abi(case)
 
 
+@pytest.mark.parametrize("case", [STRESS_CASES[1], STRESS_CASES[6]], ids=["temporal_small", "temporal_256"])
+def test_gc_unit_abi_generic_aggregation_on_mma(case, monkeypatch):
+    """DSTD_AGG_GEN_MMA=1: the opt-in mma.sync (3xTF32) forward aggregation of the shape-generic path (K >= 48)."""
+    monkeypatch.setenv("DSTD_AGG_GEN_MMA", "1")
+    test_gc_unit_abi(case)
+
+
 def test_stress_config_model_vs_oracle():
     """BASELINE.json configs[4]: H3.6M joints, 50 -> 75 frames, 256 hidden channels (DSTDGCN(6, 50, 75, ., 22, 256, 5)):
     forward and every gradient against the fp64 oracle with the fp32 oracle as yardstick (same gates as the full-size
